@@ -1,0 +1,133 @@
+"""Pins the oracle (oracle/spec.c via oracle.spec, and oracle.torch_ref) to the reference.
+
+Fixtures under tests/golden/ were produced by the unmodified reference's torch CPU path
+(tests/golden/make_golden.py).  Index ops must match exactly (FPS) or up to proven near-ties (KNN, whose
+reference fallback uses the expanded distance formula — SURVEY §8a); float ops within the stated tolerances.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec, torch_ref
+
+CORR_TOL = dict(rtol=1e-5, atol=1e-6)      # |d| <= 1e-6 + 1e-5*|ref|
+
+
+def nhwc(a):
+    return np.ascontiguousarray(np.transpose(a, (0, 2, 3, 1)))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_corr2d_forward_and_backward(golden, tag):
+    g = golden("corr2d_" + tag)
+    md = int(g["md"])
+    out = spec.corr2d_fwd(nhwc(g["feat1"]), nhwc(g["feat2"]), md)
+    np.testing.assert_allclose(out, g["out"], **CORR_TOL)
+    assert np.mean(np.abs(out - g["out"])) < 1e-6            # the reference's own criterion (correlation_test.cpp:82)
+    g1, g2 = spec.corr2d_bwd(g["grad_out"], nhwc(g["feat1"]), nhwc(g["feat2"]), md)
+    np.testing.assert_allclose(g1, g["grad1"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(g2, g["grad2"], rtol=1e-5, atol=1e-5)
+    t = torch_ref.correlation2d(torch.from_numpy(g["feat1"]), torch.from_numpy(g["feat2"]), md).numpy()
+    np.testing.assert_array_equal(t, g["out"])
+
+
+def test_fps_exact(golden):
+    g = golden("fps")
+    n = int(g["n_samples"])
+    np.testing.assert_array_equal(spec.fps(g["xyz"], n), g["idx"])
+    np.testing.assert_array_equal(torch_ref.furthest_point_sampling(torch.from_numpy(g["xyz"]), n).numpy(), g["idx"])
+
+
+def near_tie_report(inp, qry, mine, ref):
+    """Every (query, slot) where the index lists differ must be a near-tie: the fp64 distances of the two
+    candidates differ by <= 4 ulp_fp32 of max(|q|^2,|x|^2) (KNN parity check)."""
+    bad = 0
+    diff = np.argwhere(mine != ref)
+    for b, q, s in diff:
+        qq = qry[b, q].astype(np.float64)
+        da = np.sum((inp[b, mine[b, q, s]].astype(np.float64) - qq) ** 2)
+        db = np.sum((inp[b, ref[b, q, s]].astype(np.float64) - qq) ** 2)
+        scale = max(np.sum(qq ** 2), np.sum(inp[b, mine[b, q, s]].astype(np.float64) ** 2), 1e-30)
+        if abs(da - db) > 4 * np.spacing(np.float32(scale)):
+            bad += 1
+    return len(diff), bad
+
+
+@pytest.mark.parametrize("name", ["knn3d", "knn3d_k3_cf", "knn2d"])
+def test_knn_vs_reference_fallback(golden, name):
+    g = golden(name)
+    inp, qry, k = g["input"], g["query"], int(g["k"])
+    if inp.shape[1] <= 3:                                     # wrapper.py:119-122 layout sniffing
+        inp, qry = np.transpose(inp, (0, 2, 1)), np.transpose(qry, (0, 2, 1))
+    mine = spec.knn(inp, qry, k)
+    n_diff, n_bad = near_tie_report(inp, qry, mine, g["idx"])
+    assert n_bad == 0, f"{n_bad} of {n_diff} mismatches are not near-ties"
+    assert n_diff <= 0.01 * mine.size
+    t = torch_ref.k_nearest_neighbor(torch.from_numpy(g["input"]), torch.from_numpy(g["query"]), k).numpy()
+    np.testing.assert_array_equal(t, g["idx"])
+
+
+def test_knn_rule_sorted_and_tie_break():
+    rng = np.random.default_rng(0)
+    inp = rng.random((1, 64, 3), dtype=np.float32)
+    inp[0, 40] = inp[0, 3]                                    # exact duplicate: lower index must come first
+    qry = inp[:, :8].copy()
+    idx = spec.knn(inp, qry, 16)
+    d = np.sum((inp[0][idx[0]] - qry[0][:, None, :]) ** 2, -1)
+    assert np.all(np.diff(d, axis=1) >= 0)
+    assert idx[0, 3, 0] == 3 and idx[0, 3, 1] == 40
+    # M < k: trailing slots are zero (k_nearest_neighbor.cpp:16)
+    small = spec.knn(inp[:, :5], qry, 8)
+    assert np.all(small[..., 5:] == 0)
+
+
+def test_gathers_bit_exact(golden):
+    g = golden("gather_cf")
+    np.testing.assert_array_equal(spec.gather_cf(g["data"], g["idx"]), g["out"])
+    g = golden("gather_cl")
+    np.testing.assert_array_equal(spec.gather_cl(g["data"], g["idx"]), g["out"])
+
+
+def test_grid_sample_and_projection(golden):
+    g = golden("grid_sample")
+    np.testing.assert_allclose(spec.grid_sample_pts(g["feat"], g["xy"]), g["out"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(
+        torch_ref.grid_sample_wrapper(torch.from_numpy(g["feat"]), torch.from_numpy(g["xy"])).numpy(), g["out"])
+    g = golden("project_nn_corr")
+    np.testing.assert_allclose(spec.project_nn_corr(g["xy"], g["feat2d"], g["feat3d"], g["nn"]), g["out"],
+                               rtol=1e-5, atol=1e-5)
+    t = torch_ref.project_feat_with_nn_corr(*(torch.from_numpy(g[n]) for n in ("xy", "feat2d", "feat3d", "nn")))
+    np.testing.assert_array_equal(t.numpy(), g["out"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_corr3d(golden, tag):
+    g = golden("corr3d_" + tag)
+    w = {n[2:]: g[n] for n in g if n.startswith("w_")}
+    out = spec.corr3d_fwd(g["xyz1"], g["feat1"], g["xyz2"], g["feat2"], g["knn12"], g["knn11"], w)
+    scale = np.abs(g["out"]).max()
+    np.testing.assert_allclose(out, g["out"], rtol=1e-4, atol=1e-5 * scale)
+    tw = {n: torch.from_numpy(v) for n, v in w.items()}
+    t = torch_ref.correlation3d(*(torch.from_numpy(g[n]) for n in ("xyz1", "feat1", "xyz2", "feat2")), tw,
+                                k=int(g["k"]), knn11=torch.from_numpy(g["knn11"]))
+    np.testing.assert_allclose(t.numpy(), g["out"], rtol=1e-6, atol=1e-7 * scale)
+
+
+@pytest.mark.parametrize("name,pol", [("event_voxel_pol", True), ("event_voxel_nopol", False)])
+def test_event_voxel_int(golden, name, pol):
+    g = golden(name)
+    vox, bad = spec.event_voxel_int(g["events"], int(g["bins"]), int(g["H"]), int(g["W"]), pol)
+    assert bad == 0
+    np.testing.assert_allclose(vox, g["vox"], rtol=0, atol=1e-5)
+    if pol:
+        assert abs(vox.sum() - len(g["events"])) < 1e-2      # sum(voxel) = n
+    t = torch_ref.events_to_voxel(g["events"], int(g["bins"]), int(g["H"]), int(g["W"]), pol)
+    np.testing.assert_array_equal(t, g["vox"])
+
+
+@pytest.mark.parametrize("name,pol", [("event_trilinear_pol", True), ("event_trilinear_nopol", False)])
+def test_event_voxel_trilinear(golden, name, pol):
+    g = golden(name)
+    args = (g["x"], g["y"], g["t"], g["p"], int(g["bins"]), int(g["H"]), int(g["W"]), pol)
+    np.testing.assert_allclose(spec.event_voxel_trilinear(*args), g["vox"], rtol=0, atol=1e-5)
+    np.testing.assert_array_equal(torch_ref.events_to_voxel_trilinear(*args), g["vox"])
