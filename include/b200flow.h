@@ -28,10 +28,16 @@ extern "C" {
 
 typedef void* b200_stream_t;            /* a cudaStream_t; NULL = legacy default stream                */
 
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
 /* Library identification. b200_abi_version() changes whenever a signature below changes. */
-int         b200_abi_version(void);
-const char* b200_build_info(void);      /* "sm_100a; <nvcc version>; <date>"                            */
-const char* b200_last_error(void);      /* thread-local; "" if none                                    */
+B200_API int         b200_abi_version(void);
+B200_API const char* b200_build_info(void);      /* "sm_100a; <nvcc version>; <date>"                            */
+B200_API const char* b200_last_error(void);      /* thread-local; "" if none                                    */
 
 /* ------------------------------------------------------------------------------------------------------
  * a1  2-D local correlation cost volume, forward.
@@ -43,7 +49,7 @@ const char* b200_last_error(void);      /* thread-local; "" if none             
  * Every output element is written (the caller does not need to zero `out`).
  * Limits: 1 <= md <= 4 (the model uses 4), C >= 1.
  */
-int b200_corr2d_fwd(const float* in1_nhwc, const float* in2_nhwc, float* out_nchw,
+B200_API int b200_corr2d_fwd(const float* in1_nhwc, const float* in2_nhwc, float* out_nchw,
                     int B, int C, int H, int W, int md, b200_stream_t stream);
 
 /* a2  backward of a1.
@@ -52,7 +58,7 @@ int b200_corr2d_fwd(const float* in1_nhwc, const float* in2_nhwc, float* out_nch
  *   grad_out : [B,(2md+1)^2,H,W] NCHW contiguous; in1,in2 : NHWC;  gin1,gin2 : [B,C,H,W] **NCHW** (as the
  *   reference; wrapper.py:34-35 permutes them back to NHWC).
  */
-int b200_corr2d_bwd(const float* grad_out_nchw, const float* in1_nhwc, const float* in2_nhwc,
+B200_API int b200_corr2d_bwd(const float* grad_out_nchw, const float* in1_nhwc, const float* in2_nhwc,
                     float* gin1_nchw, float* gin2_nchw,
                     int B, int C, int H, int W, int md, b200_stream_t stream);
 
@@ -65,7 +71,7 @@ int b200_corr2d_bwd(const float* grad_out_nchw, const float* in1_nhwc, const flo
  * next = argmax(dist), LOWEST index on ties  == the reference torch fallback (wrapper.py:83-96) bit for bit.
  * Requires N > n_samples >= 1 (wrapper.py:98 asserts it).  No scratch needed (distances live in registers).
  */
-int b200_fps(const float* xyz, int64_t* idx, int B, int N, int n_samples, b200_stream_t stream);
+B200_API int b200_fps(const float* xyz, int64_t* idx, int B, int N, int n_samples, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * a4  k nearest neighbours (brute-force exact).
@@ -76,7 +82,7 @@ int b200_fps(const float* xyz, int64_t* idx, int B, int N, int n_samples, b200_s
  * ascending); 1 <= k <= 32 (the reference silently overruns its 32-slot arrays beyond that -> B200_EINVAL
  * here).  If M < k the trailing slots are 0 (the reference zero-initialises, k_nearest_neighbor.cpp:16).
  */
-int b200_knn(const float* input_xyz, const float* query_xyz, int64_t* idx,
+B200_API int b200_knn(const float* input_xyz, const float* query_xyz, int64_t* idx,
              int B, int M, int Q, int D, int k, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
@@ -87,9 +93,9 @@ int b200_knn(const float* input_xyz, const float* query_xyz, int64_t* idx,
  * Negative indices wrap once (idx+N) as torch indexing does; anything else out of range -> B200_EINVAL is
  * NOT detected on the device (no sync) — such indices are clamped and counted in *bad_count if non-NULL.
  */
-int b200_gather_cf(const void* data, const int64_t* idx, void* out,
+B200_API int b200_gather_cf(const void* data, const int64_t* idx, void* out,
                    int B, int C, int N, int64_t I, int* bad_count, b200_stream_t stream);
-int b200_gather_cl(const void* data, const int64_t* idx, void* out,
+B200_API int b200_gather_cl(const void* data, const int64_t* idx, void* out,
                    int B, int C, int N, int64_t I, int* bad_count, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
@@ -99,7 +105,7 @@ int b200_gather_cl(const void* data, const int64_t* idx, void* out,
  *   feat : [B,C,H,W] NCHW fp32;  xy : [B,2,N] (x row then y row, level-pixel units)  ->  out : [B,C,N]
  * Coordinates take the reference's round trip: xn = 2*x/(W-1)-1 ; ix = ((xn+1)/2)*(W-1)  (fp32).
  */
-int b200_grid_sample_pts(const float* feat_nchw, const float* xy, float* out,
+B200_API int b200_grid_sample_pts(const float* feat_nchw, const float* xy, float* out,
                          int B, int C, int H, int W, int N, b200_stream_t stream);
 
 /* a8  point -> image projection with nearest-neighbour correlation.
@@ -110,7 +116,7 @@ int b200_grid_sample_pts(const float* feat_nchw, const float* xy, float* out,
  *   out[:,3:]  = feat3d[:,nn]
  *   scratch : >= B*N*C2 floats (holds feat2d sampled at the N points, point-major).
  */
-int b200_project_nn_corr(const float* xy, const float* feat2d_nchw, const float* feat3d,
+B200_API int b200_project_nn_corr(const float* xy, const float* feat2d_nchw, const float* feat3d,
                          const int64_t* nn, float* out, float* scratch,
                          int B, int C2, int C3, int H, int W, int N, b200_stream_t stream);
 
@@ -135,8 +141,8 @@ typedef struct b200_corr3d_weights {
     const float *n2_Wa, *n2_ba, *n2_Wb, *n2_bb, *n2_Wc, *n2_bc;   /* weight_net2 (cross neighbours) */
 } b200_corr3d_weights;
 
-int64_t b200_corr3d_scratch_floats(int B, int Cin, int Cout, int N1, int N2, int k);
-int b200_corr3d_fwd(const float* xyz1, const float* feat1, const float* xyz2, const float* feat2,
+B200_API int64_t b200_corr3d_scratch_floats(int B, int Cin, int Cout, int N1, int N2, int k);
+B200_API int b200_corr3d_fwd(const float* xyz1, const float* feat1, const float* xyz2, const float* feat2,
                     const int64_t* knn12, const int64_t* knn11, const b200_corr3d_weights* w,
                     float* out, float* scratch,
                     int B, int Cin, int Cout, int N1, int N2, int k, int precision, b200_stream_t stream);
@@ -150,7 +156,7 @@ int b200_corr3d_fwd(const float* xyz1, const float* feat1, const float* xyz2, co
  *   polarity=1: channels [0,bins) count p>0 events, [bins,2*bins) count p<=0 events (both weight +1).
  *   polarity=0: one grid, weight = p (event_utils.py:247).
  */
-int b200_event_voxel_int(const float* events, int64_t n, float* vox, int bins, int H, int W,
+B200_API int b200_event_voxel_int(const float* events, int64_t n, float* vox, int bins, int H, int W,
                          int polarity, int* status, b200_stream_t stream);
 
 /* a10 event voxel grid, float pixels + tri-linear splat (DSEC).
@@ -158,7 +164,7 @@ int b200_event_voxel_int(const float* events, int64_t n, float* vox, int bins, i
  *   x,y : [n] fp32 (rectified pixel coords); t : [n] int64 (microseconds, sorted); p : [n] fp32
  *   vox : [bins*(polarity?2:1), H, W]; scratch : >= 8 ints (first/last index of each polarity subset).
  */
-int b200_event_voxel_trilinear(const float* x, const float* y, const int64_t* t, const float* p, int64_t n,
+B200_API int b200_event_voxel_trilinear(const float* x, const float* y, const int64_t* t, const float* p, int64_t n,
                                float* vox, int bins, int H, int W, int polarity, int* scratch,
                                b200_stream_t stream);
 

@@ -1,0 +1,79 @@
+// common.cuh — shared host/device helpers for libb200flow.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200flow.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libb200flow is written for sm_100a (B200) only"
+#endif
+
+namespace b200 {
+
+// ---- host-side error plumbing (thread-local message, reference: TORCH_CHECK -> RuntimeError) ----
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define B200_REQUIRE(cond, ...)                                  \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            ::b200::set_error(__VA_ARGS__);                      \
+            return B200_EINVAL;                                  \
+        }                                                        \
+    } while (0)
+
+#define B200_CUDA(call)                                          \
+    do {                                                         \
+        cudaError_t e_ = (call);                                 \
+        if (e_ != cudaSuccess) return ::b200::cuda_fail(e_, #call); \
+    } while (0)
+
+#define B200_LAUNCH_CHECK(name)                                  \
+    do {                                                         \
+        cudaError_t e_ = cudaGetLastError();                     \
+        if (e_ != cudaSuccess) return ::b200::cuda_fail(e_, name); \
+    } while (0)
+
+static inline cudaStream_t as_stream(b200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+int sm_count();   // SMs of the current device (cached per device)
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+constexpr unsigned FULL = 0xffffffffu;
+
+// The stated distance rule: every product and sum rounded separately, left to right.
+// __f*_rn intrinsics are never contracted into FFMA by nvcc.
+__device__ __forceinline__ float sqdist3_rule(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+__device__ __forceinline__ float sqdist2_rule(float ax, float ay, float bx, float by) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+// Packed fp32x2 FMA (Blackwell FFMA2): d = a*b + d on both halves.
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
+    unsigned long long dd, aa, bb;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b.x), "f"(b.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int bytes = valid ? 16 : 0;   // src-size 0 -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float leaky01(float v) { return v > 0.0f ? v : 0.1f * v; }
+#endif
+
+}  // namespace b200

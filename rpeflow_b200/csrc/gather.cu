@@ -1,0 +1,255 @@
+// gather.cu — a6/a7/a8: batched index gathers and the image<->point bilinear projection gathers.
+//
+// Replaces (all torch-op chains in the reference):
+//   a6 models/utils.py:119-137 batch_indexing_channel_first  (torch.gather with an expanded [B,C,I] int64 index:
+//      8 B of index traffic per 4 B moved) and :101-116 batch_indexing_channel_last;
+//   a7 models/utils.py:288-294 grid_sample_wrapper           (normalise + F.grid_sample on NCHW);
+//   a8 models/utils.py:297-317 project_feat_with_nn_corr     (grid_sample + 3 gathers + mul + mean + cat).
+//
+// All are HBM/L2-bandwidth bound.  Rules followed: index read ONCE per output column (not once per channel),
+// consecutive threads on the contiguous output axis (full 128-B store lines), point-major scratch for rows that
+// are later gathered so that gather reads are contiguous 128-bit loads, enough CTAs to fill 148 SMs by
+// splitting the channel loop over blockIdx.y when the point axis alone is too short.
+#include "common.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ int64_t wrap_index(int64_t j, int N, int* bad) {
+    if (j < 0) j += N;                                   // torch: negative indices wrap once
+    if (j < 0 || j >= N) {                               // torch would raise; we clamp and count
+        if (bad) atomicAdd(bad, 1);
+        j = j < 0 ? 0 : N - 1;
+    }
+    return j;
+}
+
+// out[b,c,i] = data[b,c,idx[b,i]]     grid: (ceil(I/256), csplit, B)
+__global__ void __launch_bounds__(256)
+gather_cf_kernel(const uint32_t* __restrict__ data, const int64_t* __restrict__ idx, uint32_t* __restrict__ out,
+                 int C, int N, int64_t I, int* bad) {
+    const int b = blockIdx.z;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= I) return;
+    const int64_t j = wrap_index(__ldg(idx + (size_t)b * I + i), N, blockIdx.y == 0 ? bad : nullptr);
+    const uint32_t* src = data + (size_t)b * C * N + j;
+    uint32_t* dst = out + (size_t)b * C * I + i;
+    const int cstep = gridDim.y;
+    int c = blockIdx.y;
+    for (; c + 3 * cstep < C; c += 4 * cstep) {          // 4 independent loads in flight
+        const uint32_t v0 = __ldg(src + (size_t)c * N), v1 = __ldg(src + (size_t)(c + cstep) * N);
+        const uint32_t v2 = __ldg(src + (size_t)(c + 2 * cstep) * N), v3 = __ldg(src + (size_t)(c + 3 * cstep) * N);
+        dst[(size_t)c * I] = v0; dst[(size_t)(c + cstep) * I] = v1;
+        dst[(size_t)(c + 2 * cstep) * I] = v2; dst[(size_t)(c + 3 * cstep) * I] = v3;
+    }
+    for (; c < C; c += cstep) dst[(size_t)c * I] = __ldg(src + (size_t)c * N);
+}
+
+// out[b,i,:] = data[b,idx[b,i],:]     one thread per 16-byte (VEC) or 4-byte element of the output row
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+gather_cl_kernel(const uint32_t* __restrict__ data, const int64_t* __restrict__ idx, uint32_t* __restrict__ out,
+                 int C, int N, int64_t I, int* bad) {
+    const int b = blockIdx.y;
+    const int per_row = VEC ? C / 4 : C;
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= I * per_row) return;
+    const int64_t i = e / per_row;
+    const int c = (int)(e - i * per_row);
+    const int64_t j = wrap_index(__ldg(idx + (size_t)b * I + i), N, c == 0 ? bad : nullptr);
+    if (VEC) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(data + ((size_t)b * N + j) * C) + c);
+        reinterpret_cast<uint4*>(out + ((size_t)b * I + i) * C)[c] = v;
+    } else {
+        out[((size_t)b * I + i) * C + c] = __ldg(data + ((size_t)b * N + j) * C + c);
+    }
+}
+
+// ---- bilinear taps, exactly the arithmetic of models/utils.py:290-291 followed by grid_sample(align_corners=True) ----
+struct Taps {
+    int o00, o01, o10, o11;      // offsets inside one H*W plane, -1 when the tap is outside the image (zero padding)
+    float w00, w01, w10, w11;
+};
+__device__ __forceinline__ float renorm_coord(float x, int size) {
+    const float sm1 = (float)(size - 1);
+    const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, x), sm1), 1.0f);        // 2*x/(size-1) - 1
+    return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), sm1);                  // ((g+1)/2)*(size-1)
+}
+__device__ __forceinline__ Taps make_taps(float x, float y, int H, int W) {
+    const float ix = renorm_coord(x, W), iy = renorm_coord(y, H);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float wx1 = ix - fx, wy1 = iy - fy, wx0 = (fx + 1.0f) - ix, wy0 = (fy + 1.0f) - iy;
+    // guard the float->int conversion against huge / non-finite coordinates (all taps invalid then)
+    const bool finite = fabsf(ix) < 1e9f && fabsf(iy) < 1e9f;
+    const int x0 = finite ? (int)fx : -2, y0 = finite ? (int)fy : -2, x1 = x0 + 1, y1 = y0 + 1;
+    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+    Taps t;
+    t.o00 = (vy0 && vx0) ? y0 * W + x0 : -1; t.w00 = wx0 * wy0;
+    t.o01 = (vy0 && vx1) ? y0 * W + x1 : -1; t.w01 = wx1 * wy0;
+    t.o10 = (vy1 && vx0) ? y1 * W + x0 : -1; t.w10 = wx0 * wy1;
+    t.o11 = (vy1 && vx1) ? y1 * W + x1 : -1; t.w11 = wx1 * wy1;
+    return t;
+}
+__device__ __forceinline__ float blend(const float* __restrict__ plane, const Taps& t) {
+    // same accumulation order as ATen's grid_sampler_2d (nw, ne, sw, se), out-of-image taps skipped
+    float v = 0.0f;
+    if (t.o00 >= 0) v += __ldg(plane + t.o00) * t.w00;
+    if (t.o01 >= 0) v += __ldg(plane + t.o01) * t.w01;
+    if (t.o10 >= 0) v += __ldg(plane + t.o10) * t.w10;
+    if (t.o11 >= 0) v += __ldg(plane + t.o11) * t.w11;
+    return v;
+}
+
+// a7: out[b,c,n] = bilinear(feat[b,c], xy[b,:,n])       grid: (ceil(N/256), csplit, B)
+__global__ void __launch_bounds__(256)
+grid_sample_pts_kernel(const float* __restrict__ feat, const float* __restrict__ xy, float* __restrict__ out,
+                       int C, int H, int W, int N) {
+    const int b = blockIdx.z;
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= N) return;
+    const Taps t = make_taps(__ldg(xy + ((size_t)b * 2 + 0) * N + n), __ldg(xy + ((size_t)b * 2 + 1) * N + n), H, W);
+    const size_t plane = (size_t)H * W;
+    const float* f = feat + (size_t)b * C * plane;
+    float* o = out + (size_t)b * C * N + n;
+    for (int c = blockIdx.y; c < C; c += gridDim.y) o[(size_t)c * N] = blend(f + (size_t)c * plane, t);
+}
+
+// a8, pass 1: S[b,n,c] = bilinear(feat2d[b,c], xy[b,:,n])  (point-major scratch)   block (32 points, 8 channel lanes)
+__global__ void __launch_bounds__(256)
+sample_point_major_kernel(const float* __restrict__ feat, const float* __restrict__ xy, float* __restrict__ S,
+                          int C, int H, int W, int N) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * 32;
+    const int tp = threadIdx.x & 31, tc = threadIdx.x >> 5;          // compute: lane = point, warp = channel lane
+    const int n = n0 + tp;
+    const bool ok = n < N;
+    Taps t = {-1, -1, -1, -1, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (ok) t = make_taps(__ldg(xy + ((size_t)b * 2 + 0) * N + n), __ldg(xy + ((size_t)b * 2 + 1) * N + n), H, W);
+    const size_t plane = (size_t)H * W;
+    const float* f = feat + (size_t)b * C * plane;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = c0 + tc * 4 + u;
+            tile[tc * 4 + u][tp] = (ok && c < C) ? blend(f + (size_t)c * plane, t) : 0.0f;
+        }
+        __syncthreads();
+        // write: lane = channel (contiguous in S), warp = 4 points
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = tc * 4 + u, c = c0 + tp;
+            if (n0 + p < N && c < C) S[((size_t)b * N + n0 + p) * C + c] = tile[tp][p];
+        }
+    }
+}
+
+// a8, pass 2: one thread per pixel.
+__global__ void __launch_bounds__(256)
+project_nn_corr_kernel(const float* __restrict__ xy, const float* __restrict__ feat2d, const float* __restrict__ feat3d,
+                       const int64_t* __restrict__ nn, const float* __restrict__ S, float* __restrict__ out,
+                       int C2, int C3, int H, int W, int N) {
+    const int b = blockIdx.y;
+    const int HW = H * W;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= HW) return;
+    int64_t j = __ldg(nn + (size_t)b * HW + p);
+    if (j < 0) j += N;
+    j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+    const float px = (float)(p % W), py = (float)(p / W);              // mesh_grid: x in channel 0 (models/utils.py:177-179)
+    float* o = out + (size_t)b * (C3 + 3) * HW + p;
+    o[0] = __ldg(xy + ((size_t)b * 2 + 0) * N + j) - px;
+    o[(size_t)HW] = __ldg(xy + ((size_t)b * 2 + 1) * N + j) - py;
+
+    const float* s = S + ((size_t)b * N + j) * C2;
+    const float* f = feat2d + (size_t)b * C2 * HW + p;
+    float acc = 0.0f;
+    int c = 0;
+    if ((C2 & 3) == 0) {
+        for (; c < C2; c += 4) {                                        // 128-bit reads of the gathered row
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(s + c));
+            acc += sv.x * __ldg(f + (size_t)(c + 0) * HW);
+            acc += sv.y * __ldg(f + (size_t)(c + 1) * HW);
+            acc += sv.z * __ldg(f + (size_t)(c + 2) * HW);
+            acc += sv.w * __ldg(f + (size_t)(c + 3) * HW);
+        }
+    } else {
+        for (; c < C2; ++c) acc += __ldg(s + c) * __ldg(f + (size_t)c * HW);
+    }
+    o[(size_t)2 * HW] = __fdiv_rn(acc, (float)C2);                      // torch.mean over channels
+
+    const float* g = feat3d + (size_t)b * C3 * N + j;
+    for (int k = 0; k < C3; ++k) o[(size_t)(3 + k) * HW] = __ldg(g + (size_t)k * N);
+}
+
+static int pick_csplit(int64_t cols, int B, int C) {
+    const int64_t ctas = (int64_t)ceil_div(cols, 256) * B;
+    const int64_t want = (int64_t)sm_count() * 4;
+    int64_t s = (want + ctas - 1) / ctas;
+    if (s < 1) s = 1;
+    if (s > C) s = C;
+    if (s > 65535) s = 65535;
+    return (int)s;
+}
+
+}  // namespace b200
+
+extern "C" int b200_gather_cf(const void* data, const int64_t* idx, void* out, int B, int C, int N, int64_t I,
+                              int* bad_count, b200_stream_t stream) {
+    using namespace b200;
+    B200_REQUIRE(data && idx && out, "b200_gather_cf: null pointer");
+    B200_REQUIRE(B >= 0 && C >= 0 && N >= 1 && I >= 0, "b200_gather_cf: bad sizes");
+    B200_REQUIRE(B <= 65535, "b200_gather_cf: B exceeds the grid limit");
+    if (B == 0 || C == 0 || I == 0) return B200_OK;
+    dim3 grid(ceil_div(I, 256), pick_csplit(I, B, C), B);
+    gather_cf_kernel<<<grid, 256, 0, as_stream(stream)>>>((const uint32_t*)data, idx, (uint32_t*)out, C, N, I, bad_count);
+    B200_LAUNCH_CHECK("b200_gather_cf");
+    return B200_OK;
+}
+
+extern "C" int b200_gather_cl(const void* data, const int64_t* idx, void* out, int B, int C, int N, int64_t I,
+                              int* bad_count, b200_stream_t stream) {
+    using namespace b200;
+    B200_REQUIRE(data && idx && out, "b200_gather_cl: null pointer");
+    B200_REQUIRE(B >= 0 && C >= 0 && N >= 1 && I >= 0, "b200_gather_cl: bad sizes");
+    B200_REQUIRE(B <= 65535, "b200_gather_cl: B exceeds the grid limit");
+    if (B == 0 || C == 0 || I == 0) return B200_OK;
+    const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int64_t elems = I * (vec ? C / 4 : C);
+    dim3 grid(ceil_div(elems, 256), B);
+    if (vec) gather_cl_kernel<true><<<grid, 256, 0, as_stream(stream)>>>((const uint32_t*)data, idx, (uint32_t*)out, C, N, I, bad_count);
+    else     gather_cl_kernel<false><<<grid, 256, 0, as_stream(stream)>>>((const uint32_t*)data, idx, (uint32_t*)out, C, N, I, bad_count);
+    B200_LAUNCH_CHECK("b200_gather_cl");
+    return B200_OK;
+}
+
+extern "C" int b200_grid_sample_pts(const float* feat, const float* xy, float* out, int B, int C, int H, int W, int N,
+                                    b200_stream_t stream) {
+    using namespace b200;
+    B200_REQUIRE(feat && xy && out, "b200_grid_sample_pts: null pointer");
+    B200_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1 && N >= 0, "b200_grid_sample_pts: bad sizes");
+    B200_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, "b200_grid_sample_pts: plane or batch too large");
+    if (B == 0 || C == 0 || N == 0) return B200_OK;
+    dim3 grid(ceil_div(N, 256), pick_csplit(N, B, C), B);
+    grid_sample_pts_kernel<<<grid, 256, 0, as_stream(stream)>>>(feat, xy, out, C, H, W, N);
+    B200_LAUNCH_CHECK("b200_grid_sample_pts");
+    return B200_OK;
+}
+
+extern "C" int b200_project_nn_corr(const float* xy, const float* feat2d, const float* feat3d, const int64_t* nn,
+                                    float* out, float* scratch, int B, int C2, int C3, int H, int W, int N,
+                                    b200_stream_t stream) {
+    using namespace b200;
+    B200_REQUIRE(xy && feat2d && feat3d && nn && out && scratch, "b200_project_nn_corr: null pointer");
+    B200_REQUIRE(B >= 0 && C2 >= 1 && C3 >= 0 && H >= 1 && W >= 1 && N >= 1, "b200_project_nn_corr: bad sizes");
+    B200_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, "b200_project_nn_corr: plane or batch too large");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "b200_project_nn_corr: scratch must be 16-byte aligned");
+    if (B == 0) return B200_OK;
+    cudaStream_t st = as_stream(stream);
+    sample_point_major_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, st>>>(feat2d, xy, scratch, C2, H, W, N);
+    B200_LAUNCH_CHECK("b200_project_nn_corr(sample)");
+    project_nn_corr_kernel<<<dim3(ceil_div((int64_t)H * W, 256), B), 256, 0, st>>>(xy, feat2d, feat3d, nn, scratch, out,
+                                                                                 C2, C3, H, W, N);
+    B200_LAUNCH_CHECK("b200_project_nn_corr");
+    return B200_OK;
+}

@@ -1,0 +1,104 @@
+"""Wire the sm_100a kernels into an UNMODIFIED checkout of danqu130/RPEFlow.
+
+    import sys; sys.path.insert(0, "/path/to/RPEFlow")
+    import rpeflow_b200.install as b200; b200.install()        # BEFORE the first `import models`
+    from models.RPEFlow import RPEFlow                          # wrapper.py now finds its three extensions
+
+What ``install()`` does
+1. registers ``models.csrc._correlation_cuda``, ``models.csrc._furthest_point_sampling_cuda`` and
+   ``models.csrc._k_nearest_neighbor_cuda`` in ``sys.modules`` (the shims in rpeflow_b200/shims), so the
+   byte-for-byte unchanged ``models/csrc/wrapper.py:4-8`` imports them instead of falling back to torch;
+2. (``patch_python_ops=True``) re-binds the pure-python hot ops that have no extension boundary in the
+   reference — ``batch_indexing_channel_{first,last}``, ``grid_sample_wrapper``, ``project_feat_with_nn_corr``
+   (models/utils.py) in every module that imported them by name, ``Correlation3D.forward``
+   (models/pwc3d_core.py:69) for inference, ``event_utils.eventsToVoxel`` and
+   ``dsec.DSECTrain.eventsToVoxelInter``.  Gathers keep the torch path for tensors that require grad.
+"""
+import importlib
+import sys
+
+import torch
+
+from . import events, ops, projection, pwc3d
+from .shims import _correlation_cuda, _furthest_point_sampling_cuda, _k_nearest_neighbor_cuda
+
+_SHIMS = {
+    "models.csrc._correlation_cuda": _correlation_cuda,
+    "models.csrc._furthest_point_sampling_cuda": _furthest_point_sampling_cuda,
+    "models.csrc._k_nearest_neighbor_cuda": _k_nearest_neighbor_cuda,
+}
+
+
+def register_extension_shims():
+    if "models.csrc.wrapper" in sys.modules:
+        raise RuntimeError("rpeflow_b200.install() must run before `models.csrc` is first imported "
+                           "(wrapper.py binds the extension symbols at import time)")
+    for name, mod in _SHIMS.items():
+        sys.modules[name] = mod
+
+
+def _grad_aware(fast, slow):
+    """Use the CUDA kernel unless autograd needs to differentiate through the op or the data is not on a GPU."""
+    def op(data, *rest):
+        if not data.is_cuda or (torch.is_grad_enabled() and data.requires_grad):
+            return slow(data, *rest)
+        return fast(data, *rest)
+    op.__name__ = fast.__name__
+    op.__doc__ = fast.__doc__
+    return op
+
+
+def _corr3d_forward(self, xyz1, feat1, xyz2, feat2, knn_indices_1in1=None):
+    needs_graph = torch.is_grad_enabled() and (feat1.requires_grad or feat2.requires_grad or
+                                               any(p.requires_grad for p in self.parameters()))
+    if needs_graph or not feat1.is_cuda:
+        return self._b200_reference_forward(xyz1, feat1, xyz2, feat2, knn_indices_1in1)
+    knn12 = ops.k_nearest_neighbor(input_xyz=xyz2, query_xyz=xyz1, k=self.k)
+    if knn_indices_1in1 is None:
+        knn_indices_1in1 = ops.k_nearest_neighbor(input_xyz=xyz1, query_xyz=xyz1, k=self.k)
+    return pwc3d.correlation3d_forward(xyz1, feat1, xyz2, feat2, pwc3d.pack_weights(self), knn12, knn_indices_1in1,
+                                       getattr(self, "b200_precision", 0))
+
+
+def patch_python_ops(patch_events=True):
+    mutils = importlib.import_module("models.utils")
+    replaced = {
+        "batch_indexing_channel_first": _grad_aware(projection.batch_indexing_channel_first,
+                                                    mutils.batch_indexing_channel_first),
+        "batch_indexing_channel_last": _grad_aware(projection.batch_indexing_channel_last,
+                                                   mutils.batch_indexing_channel_last),
+        "grid_sample_wrapper": _grad_aware(projection.grid_sample_wrapper, mutils.grid_sample_wrapper),
+        "project_feat_with_nn_corr": projection.project_feat_with_nn_corr if torch.cuda.is_available()
+        else mutils.project_feat_with_nn_corr,
+    }
+    for modname in ("models.utils", "models.RPEFlow_core", "models.pwc3d_core", "models.pointconv",
+                    "models.losses3d", "models.RPEFlow"):
+        try:
+            mod = importlib.import_module(modname)
+        except Exception:
+            continue
+        for name, fn in replaced.items():
+            if hasattr(mod, name):
+                setattr(mod, name, fn)
+    core = importlib.import_module("models.pwc3d_core")
+    if not hasattr(core.Correlation3D, "_b200_reference_forward"):
+        core.Correlation3D._b200_reference_forward = core.Correlation3D.forward
+        core.Correlation3D.forward = _corr3d_forward
+    if patch_events:
+        for modname, attr, fn in (("event_utils", "eventsToVoxel", events.eventsToVoxel),):
+            try:
+                setattr(importlib.import_module(modname), attr, fn)
+            except Exception:
+                pass
+        try:
+            dsec = importlib.import_module("dsec")
+            dsec.DSECTrain.eventsToVoxelInter = lambda self, ev, num_bins, height, width, event_polarity=False: \
+                events.eventsToVoxelInter(ev, num_bins, height, width, event_polarity)
+        except Exception:
+            pass
+
+
+def install(patch_python=True, patch_events=False):
+    register_extension_shims()
+    if patch_python:
+        patch_python_ops(patch_events=patch_events)

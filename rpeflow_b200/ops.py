@@ -1,0 +1,157 @@
+"""Host-side mirror of the reference's operator API for the cost-volume hot path.
+
+Same names, argument meaning and return types as ``models/csrc/wrapper.py`` of danqu130/RPEFlow
+(``correlation2d`` :55-72, ``furthest_point_sampling`` :75-103, ``k_nearest_neighbor`` :106-127,
+``squared_distance`` :40-52, ``CorrelationFunction`` :18-37) and as the three pybind modules it imports
+(``_correlation_forward_cuda`` / ``_correlation_backward_cuda`` correlation.cpp:38-41,
+``_furthest_point_sampling_cuda`` furthest_point_sampling.cpp:19-21, ``_k_nearest_neighbor_cuda``
+k_nearest_neighbor.cpp:27-29), but every op runs a hand-written sm_100a kernel through the C-ABI of
+include/b200flow.h.  PyTorch is only used to own device memory and name the stream.
+
+Differences from the reference, all deliberate:
+* CUDA only.  There is no torch/CPU fallback: CPU tensors raise RuntimeError.
+* Launches go to torch's *current* stream on the tensor's device (the reference uses the legacy default stream).
+* ``k > 32`` raises (the reference overruns its 32-slot arrays); CUDA launch errors are reported.
+* Exactness rules for FPS/KNN are the ones stated in include/b200flow.h.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+__all__ = [
+    "correlation2d", "furthest_point_sampling", "k_nearest_neighbor", "squared_distance", "CorrelationFunction",
+    "_correlation_forward_cuda", "_correlation_backward_cuda", "_furthest_point_sampling_cuda",
+    "_k_nearest_neighbor_cuda",
+]
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)          # what TORCH_CHECK raises on the reference side
+
+
+def _cuda_f32(t, name):
+    _require(isinstance(t, torch.Tensor), f"{name} must be a tensor")
+    _require(t.is_cuda, f"{name} must be a CUDA tensor")
+    _require(t.dtype == torch.float32, f"{name} must be a float tensor")
+    _require(t.is_contiguous(), f"{name} must be a contiguous tensor")
+
+
+# ------------------------------------------------------------------------------------------ extension-level API
+def _correlation_forward_cuda(input1, input2, max_displacement):
+    """input1/input2 [B,H,W,C] NHWC -> [B,(2md+1)^2,H,W]  (replaces correlation.cpp:11-22)."""
+    _cuda_f32(input1, "input1")
+    _cuda_f32(input2, "input2")
+    _require(input1.shape == input2.shape and input1.dim() == 4, "input1/input2 must both be [B,H,W,C]")
+    B, H, W, C = input1.shape
+    md = int(max_displacement)
+    out = torch.empty((B, (2 * md + 1) ** 2, H, W), dtype=torch.float32, device=input1.device)
+    with torch.cuda.device(input1.device):
+        check(lib.b200_corr2d_fwd(input1.data_ptr(), input2.data_ptr(), out.data_ptr(), B, C, H, W, md,
+                                  _stream(input1)), "b200_corr2d_fwd")
+    return out
+
+
+def _correlation_backward_cuda(grad_output, input1, input2, max_displacement):
+    """-> (grad_input1, grad_input2), both [B,C,H,W] NCHW as the reference (correlation.cpp:24-35)."""
+    _cuda_f32(input1, "input1")
+    _cuda_f32(input2, "input2")
+    grad_output = grad_output.contiguous().float()      # the reference forgets this check
+    B, H, W, C = input1.shape
+    md = int(max_displacement)
+    _require(tuple(grad_output.shape) == (B, (2 * md + 1) ** 2, H, W), "grad_output has the wrong shape")
+    g1 = torch.empty((B, C, H, W), dtype=torch.float32, device=input1.device)
+    g2 = torch.empty_like(g1)
+    with torch.cuda.device(input1.device):
+        check(lib.b200_corr2d_bwd(grad_output.data_ptr(), input1.data_ptr(), input2.data_ptr(), g1.data_ptr(),
+                                  g2.data_ptr(), B, C, H, W, md, _stream(input1)), "b200_corr2d_bwd")
+    return g1, g2
+
+
+def _furthest_point_sampling_cuda(points_xyz, n_samples):
+    """points_xyz [B,N,3] -> [B,n_samples] int64 (replaces furthest_point_sampling.cpp:5-16)."""
+    _cuda_f32(points_xyz, "points_xyz")
+    _require(points_xyz.dim() == 3 and points_xyz.shape[2] == 3, "points_xyz must be [B,N,3]")
+    B, N, _ = points_xyz.shape
+    out = torch.empty((B, int(n_samples)), dtype=torch.int64, device=points_xyz.device)
+    with torch.cuda.device(points_xyz.device):
+        check(lib.b200_fps(points_xyz.data_ptr(), out.data_ptr(), B, N, int(n_samples), _stream(points_xyz)),
+              "b200_fps")
+    return out
+
+
+def _k_nearest_neighbor_cuda(input_xyz, query_xyz, k):
+    """input [B,M,D], query [B,Q,D] -> [B,Q,k] int64 (replaces k_nearest_neighbor.cpp:6-24)."""
+    _cuda_f32(input_xyz, "input_xyz")
+    _cuda_f32(query_xyz, "query_xyz")
+    _require(input_xyz.dim() == 3 and query_xyz.dim() == 3 and input_xyz.shape[0] == query_xyz.shape[0]
+             and input_xyz.shape[2] == query_xyz.shape[2], "input_xyz/query_xyz must be [B,M,D]/[B,Q,D]")
+    B, M, D = input_xyz.shape
+    Q = query_xyz.shape[1]
+    out = torch.empty((B, Q, int(k)), dtype=torch.int64, device=query_xyz.device)
+    with torch.cuda.device(query_xyz.device):
+        check(lib.b200_knn(input_xyz.data_ptr(), query_xyz.data_ptr(), out.data_ptr(), B, M, Q, D, int(k),
+                           _stream(query_xyz)), "b200_knn")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ wrapper-level API
+class CorrelationFunction(torch.autograd.Function):
+    """NHWC in, NCHW out; gradients returned NHWC (wrapper.py:18-37)."""
+
+    @staticmethod
+    def forward(ctx, input1, input2, max_displacement):
+        ctx.save_for_backward(input1, input2)
+        ctx.max_displacement = max_displacement
+        return _correlation_forward_cuda(input1, input2, max_displacement)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input1, input2 = ctx.saved_tensors
+        g1, g2 = _correlation_backward_cuda(grad_output, input1, input2, ctx.max_displacement)
+        return g1.permute(0, 2, 3, 1).contiguous(), g2.permute(0, 2, 3, 1).contiguous(), None
+
+
+def _no_fallback(name, *tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError(f"rpeflow_b200.{name}: CUDA tensors required — this build has no CPU/torch fallback")
+
+
+def correlation2d(input1, input2, max_displacement, cpp_impl=True):
+    """input1, input2 [B,C,H,W] -> [B,(2md+1)^2,H,W] (wrapper.py:55-72). cpp_impl is accepted and ignored."""
+    _no_fallback("correlation2d", input1, input2)
+    input1 = input1.permute(0, 2, 3, 1).contiguous().float()
+    input2 = input2.permute(0, 2, 3, 1).contiguous().float()
+    return CorrelationFunction.apply(input1, input2, max_displacement)
+
+
+def furthest_point_sampling(xyz, n_samples, cpp_impl=True):
+    """xyz [B,N,3] -> [B,n_samples] int64 (wrapper.py:75-103)."""
+    assert xyz.shape[2] == 3 and xyz.shape[1] > n_samples        # wrapper.py:98
+    _no_fallback("furthest_point_sampling", xyz)
+    return _furthest_point_sampling_cuda(xyz.contiguous(), n_samples).to(torch.int64)
+
+
+def k_nearest_neighbor(input_xyz, query_xyz, k, cpp_impl=True):
+    """[B,N,D] or [B,D,N] (D<=3, sniffed like wrapper.py:119-122) -> [B,Q,k] int64 (wrapper.py:106-127)."""
+    _no_fallback("k_nearest_neighbor", input_xyz, query_xyz)
+    if input_xyz.shape[1] <= 3:
+        assert query_xyz.shape[1] == input_xyz.shape[1]
+        input_xyz = input_xyz.transpose(1, 2).contiguous()
+        query_xyz = query_xyz.transpose(1, 2).contiguous()
+    return _k_nearest_neighbor_cuda(input_xyz.contiguous(), query_xyz.contiguous(), k)
+
+
+def squared_distance(xyz1, xyz2):
+    """[B,N1,D],[B,N2,D] -> [B,N1,N2]; kept for API completeness (wrapper.py:40-52); not on the CUDA hot path."""
+    assert xyz1.shape[-1] == xyz2.shape[-1] and xyz1.shape[-1] <= 3
+    dist = -2 * torch.matmul(xyz1, xyz2.permute(0, 2, 1))
+    dist += torch.sum(xyz1 ** 2, -1).unsqueeze(2)
+    dist += torch.sum(xyz2 ** 2, -1).unsqueeze(1)
+    return dist

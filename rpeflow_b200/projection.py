@@ -1,0 +1,108 @@
+"""Drop-in replacements for the reference's gather / projection helpers (models/utils.py of danqu130/RPEFlow).
+
+Same signatures and return shapes as ``batch_indexing_channel_first`` (:119-137), ``batch_indexing_channel_last``
+(:101-116), ``grid_sample_wrapper`` (:288-294) and ``project_feat_with_nn_corr`` (:297-317); each is one or two
+sm_100a kernels behind include/b200flow.h.  Forward only: the reference calls the last two under
+``torch.no_grad()`` everywhere (RPEFlow_core.py:52,105,156; models/utils.py:297), and the gathers are used on
+index/geometry tensors.  When autograd needs a gradient through a gather, keep the torch version.
+"""
+import torch
+
+from ._lib import check, lib
+
+__all__ = ["batch_indexing_channel_first", "batch_indexing_channel_last", "grid_sample_wrapper",
+           "project_feat_with_nn_corr"]
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _prep_data(data, name):
+    if not data.is_cuda:
+        raise RuntimeError(f"rpeflow_b200.{name}: CUDA tensors required — no CPU/torch fallback")
+    if data.element_size() != 4:
+        raise RuntimeError(f"rpeflow_b200.{name}: only 4-byte element types are supported (got {data.dtype})")
+    return data.contiguous()
+
+
+def _prep_idx(idx, device):
+    return idx.to(device=device, dtype=torch.int64).contiguous()
+
+
+def batch_indexing_channel_first(batched_data, batched_indices):
+    """[B,C,N], [B,I1..Im] -> [B,C,I1..Im] (bit-exact move of 4-byte elements)."""
+    assert batched_data.shape[0] == batched_indices.shape[0]
+    data = _prep_data(batched_data, "batch_indexing_channel_first")
+    if data.dim() != 3:
+        raise RuntimeError("batch_indexing_channel_first expects data of shape [B,C,N]")
+    idx = _prep_idx(batched_indices, data.device)
+    B, C, N = data.shape
+    I = idx.numel() // max(B, 1)
+    out = torch.empty((B, C, I), dtype=data.dtype, device=data.device)
+    with torch.cuda.device(data.device):
+        check(lib.b200_gather_cf(data.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, I, None, _stream(data)),
+              "b200_gather_cf")
+    return out.view([B, C] + list(idx.shape[1:]))
+
+
+def batch_indexing_channel_last(batched_data, batched_indices):
+    """[B,N,C] (or [B,N]), [B,I1..Im] -> [B,I1..Im,C] (or [B,I1..Im])."""
+    assert batched_data.shape[0] == batched_indices.shape[0]
+    data = _prep_data(batched_data, "batch_indexing_channel_last")
+    flat = data.dim() == 2
+    if flat:
+        data = data.unsqueeze(-1)
+    if data.dim() != 3:
+        raise RuntimeError("batch_indexing_channel_last expects data of shape [B,N,C] or [B,N]")
+    idx = _prep_idx(batched_indices, data.device)
+    B, N, C = data.shape
+    I = idx.numel() // max(B, 1)
+    out = torch.empty((B, I, C), dtype=data.dtype, device=data.device)
+    with torch.cuda.device(data.device):
+        check(lib.b200_gather_cl(data.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, I, None, _stream(data)),
+              "b200_gather_cl")
+    shape = [B] + list(idx.shape[1:])
+    return out.view(shape) if flat else out.view(shape + [C])
+
+
+def grid_sample_wrapper(feat_2d, xy):
+    """feat_2d [B,C,H,W], xy [B,2,N] (pixels) -> [B,C,N]; bilinear, align_corners=True, zero padding."""
+    if not (feat_2d.is_cuda and xy.is_cuda):
+        raise RuntimeError("rpeflow_b200.grid_sample_wrapper: CUDA tensors required — no CPU/torch fallback")
+    feat = feat_2d.contiguous().float()
+    pts = xy.contiguous().float()
+    B, C, H, W = feat.shape
+    N = pts.shape[2]
+    out = torch.empty((B, C, N), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        check(lib.b200_grid_sample_pts(feat.data_ptr(), pts.data_ptr(), out.data_ptr(), B, C, H, W, N,
+                                       _stream(feat)), "b200_grid_sample_pts")
+    return out
+
+
+@torch.no_grad()
+def project_feat_with_nn_corr(xy, feat_2d, feat_3d, nn_indices=None):
+    """xy [B,2,N], feat_2d [B,C2,H,W], feat_3d [B,C3,N], nn_indices [B,H*W] -> [B,C3+3,H,W]."""
+    if not (xy.is_cuda and feat_2d.is_cuda and feat_3d.is_cuda):
+        raise RuntimeError("rpeflow_b200.project_feat_with_nn_corr: CUDA tensors required — no CPU/torch fallback")
+    f2 = feat_2d.contiguous().float()
+    f3 = feat_3d.contiguous().float()
+    pts = xy.contiguous().float()
+    B, C2, H, W = f2.shape
+    C3, N = f3.shape[1], f3.shape[2]
+    if nn_indices is None:                              # models/utils.py:304-305: nearest projected point per pixel
+        from .ops import k_nearest_neighbor
+        ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=f2.device),
+                                torch.arange(W, dtype=torch.float32, device=f2.device), indexing="ij")
+        grid = torch.stack([xs, ys], 0).reshape(1, 2, H * W).expand(B, 2, H * W)
+        nn_indices = k_nearest_neighbor(pts, grid, k=1)[..., 0]
+    else:
+        assert tuple(nn_indices.shape) == (B, H * W)
+    nn = _prep_idx(nn_indices, f2.device)
+    out = torch.empty((B, C3 + 3, H, W), dtype=torch.float32, device=f2.device)
+    scratch = torch.empty((B, N, C2), dtype=torch.float32, device=f2.device)
+    with torch.cuda.device(f2.device):
+        check(lib.b200_project_nn_corr(pts.data_ptr(), f2.data_ptr(), f3.data_ptr(), nn.data_ptr(), out.data_ptr(),
+                                       scratch.data_ptr(), B, C2, C3, H, W, N, _stream(f2)), "b200_project_nn_corr")
+    return out
