@@ -62,7 +62,8 @@ def _load():
 
 
 lib = _load()
-LAUNCHES = 0          # kernels-launching C-ABI calls made by this process (bench.py reports it)
+LAUNCHES = 0          # kernels of this library launched by this process (bench.py reports it as gpu_launches)
+KERNELS_PER_CALL = {"b200_corr2d_bwd": 2, "b200_project_nn_corr": 2, "b200_corr3d_fwd": 5, "b200_event_voxel_trilinear": 3}
 
 
 class B200Error(RuntimeError):
@@ -72,6 +73,6 @@ class B200Error(RuntimeError):
 def check(rc, what):
     """0 -> ok; otherwise raise RuntimeError like the reference's TORCH_CHECK does."""
     global LAUNCHES
-    LAUNCHES += 1
+    LAUNCHES += KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         raise B200Error(f"{what} failed ({rc}): {lib.b200_last_error().decode()}")

@@ -1,0 +1,318 @@
+"""The cost-volume stack: one replay of the hot-op census of a RPEFlow forward pass for a batch of frame pairs.
+
+This is the workload behind BASELINE.json's metric (frame-pairs/s through corr2d + KNN/FPS + 3-D cost volume +
+projection gathers + event voxels).  The census follows the reference call by call (file:line in
+danqu130/RPEFlow):
+
+  event voxel grid                      1x  event_utils.py:109 (things/kubric) or dsec.py:570 (dsec)
+  build_pc_pyramid                      1x FPS on cat[pc1,pc2] -> 4096, 10 xyz gathers      pwc3d_core.py:8-28
+  FeaturePyramid3D (2 clouds)          10x KNN k=16 (8192->4096 ... 512->256)               pointconv.py:46
+  decode, level 5..1 (RPEFlow_core.py:307-395)
+      2x KNN 2-D k=1 (pixel grid -> projected points)   :329-330        1x KNN self k=16      :331
+      2x project_feat_with_nn_corr (C_l, C_l)           :334-335        2x grid_sample (C_l)  :336-337
+      [l<5] 2x KNN k=3 (knn_interpolation, backwarp_3d) :354-358
+      Correlation3D (KNN cross k=16 inside)             :361            correlation2d md=4    :362
+      project_feat_with_nn_corr (81, C_l+2)             :373            2x grid_sample (83, C_l event)  :376
+      project_feat_with_nn_corr (96, 64)                :394            grid_sample (96)      :395
+  final upsampling                      5x KNN k=3 (N_{l+1} -> N_l)                          :429-430
+
+= 1 voxelisation, 1 FPS, 43 KNN, 5 corr2d, 5 Correlation3D, 20 project_feat_with_nn_corr (whose internal
+grid_sample is fused) + 25 stand-alone grid_sample_wrapper.  Everything between those calls (convolutions,
+attention, flow heads) is out of scope, so the feature maps the ops consume are synthetic activations.
+"""
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import events as _events
+from . import ops, projection, pwc3d
+
+LEVEL_CHANNELS = [32, 64, 96, 128, 192]          # levels 1..5 (pwc2d_core.py:28-40 / pwc3d_core.py:44-57)
+PYRAMID_POINTS = [4096, 2048, 1024, 512, 256]    # RPEFlow.py:74 (hard-coded)
+
+
+@dataclass
+class StackConfig:
+    name: str = "things"          # "things" (cfg1, integer-pixel voxels) | "dsec" (cfg4, tri-linear voxels)
+    height: int = 540
+    width: int = 960
+    n_points: int = 8192
+    n_events: int = 1_000_000
+    event_bins: int = 10
+    k: int = 16
+    max_displacement: int = 4
+    focal: float = 1050.0
+    max_depth: float = 35.0
+    precision: int = 0            # Correlation3D arithmetic (include/b200flow.h)
+
+    @property
+    def padded(self):             # resize_to_64x (models/utils.py:227-241)
+        return (self.height + 63) // 64 * 64, (self.width + 63) // 64 * 64
+
+    def level_hw(self, level):    # level 1..5 -> feature map size
+        h, w = self.padded
+        return h >> (level + 1), w >> (level + 1)
+
+    @property
+    def sensor(self):             # IDS parallel sensor (conf/test/things.yaml:18-20: divisor 32)
+        h, w = self.padded
+        return h // 32, w // 32
+
+
+CONFIGS = {
+    "things": StackConfig(),
+    "dsec": StackConfig(name="dsec", height=480, width=640, n_events=1_500_000, focal=1050.0 * 640 / 960),
+    "hd": StackConfig(name="hd", height=1080, width=1920, n_points=32768, n_events=4_000_000, focal=2100.0),
+    "tiny": StackConfig(name="tiny", height=128, width=192, n_points=8192, n_events=20_000),
+}
+
+
+def make_host_inputs(cfg, batch, first_sample=0, seed_base=1000, pin=False):
+    """Synthetic inputs for `batch` frame pairs (sample i is seeded seed_base + first_sample + i, so a shard can be
+    regenerated anywhere).  Everything lives in host memory (pinned on request): point clouds already in the
+    model's parallel-projection coordinates (models/utils.py:320-346), raw events, and the activations the hot
+    ops consume."""
+    hs, ws = cfg.sensor
+    hp, wp = cfg.padded
+    out = {"pcs": torch.empty(batch, 6, cfg.n_points), "feat2d": {}, "efeat2d": {}, "feat3d": {}, "flowfeat": {}}
+    if cfg.name == "dsec":
+        out["ev_x"] = torch.empty(batch, cfg.n_events)
+        out["ev_y"] = torch.empty(batch, cfg.n_events)
+        out["ev_p"] = torch.empty(batch, cfg.n_events)
+        out["ev_t"] = torch.empty(batch, cfg.n_events, dtype=torch.int64)
+    else:
+        out["events"] = torch.empty(batch, cfg.n_events, 4)
+    for lvl, c in zip(range(1, 6), LEVEL_CHANNELS):
+        h, w = cfg.level_hw(lvl)
+        n = PYRAMID_POINTS[lvl - 1]
+        out["feat2d"][lvl] = (torch.empty(batch, c, h, w), torch.empty(batch, c, h, w))   # image 1 / image 2 features
+        out["efeat2d"][lvl] = torch.empty(batch, c, h, w)             # event features
+        out["feat3d"][lvl] = (torch.empty(batch, c, n), torch.empty(batch, c, n))
+        out["flowfeat"][lvl] = (torch.empty(batch, 96, h, w), torch.empty(batch, 64, n))   # decoder features (pwc2d_core.py:119)
+    scale_w, scale_h = (ws - 1) / (wp - 1), (hs - 1) / (hp - 1)
+    for i in range(batch):
+        g = torch.Generator().manual_seed(seed_base + first_sample + i)
+        for half in range(2):     # FT3D-shaped cloud -> perspective projection -> IDS parallel coordinates
+            u = torch.rand(cfg.n_points, generator=g) * (cfg.width - 1)
+            v = torch.rand(cfg.n_points, generator=g) * (cfg.height - 1)
+            z = torch.rand(cfg.n_points, generator=g) * (cfg.max_depth - 2.0) + 2.0
+            out["pcs"][i, 3 * half + 0] = u * (wp - 1) / (cfg.width - 1) * scale_w - (ws - 1) / 2
+            out["pcs"][i, 3 * half + 1] = v * (hp - 1) / (cfg.height - 1) * scale_h - (hs - 1) / 2
+            out["pcs"][i, 3 * half + 2] = (cfg.focal * torch.log(z) + 1.0) * min(scale_w, scale_h)
+        n = cfg.n_events
+        if cfg.name == "dsec":
+            out["ev_x"][i] = torch.rand(n, generator=g) * (cfg.width - 1)
+            out["ev_y"][i] = torch.rand(n, generator=g) * (cfg.height - 1)
+            out["ev_t"][i] = torch.sort(torch.randint(0, 100_000, (n,), generator=g)).values
+            out["ev_p"][i] = torch.randint(0, 2, (n,), generator=g).float()
+        else:
+            ev = out["events"][i]
+            ev[:, 0] = torch.randint(0, cfg.width, (n,), generator=g).float()
+            ev[:, 1] = torch.randint(0, cfg.height, (n,), generator=g).float()
+            ev[:, 2] = torch.sort(torch.rand(n, generator=g)).values
+            ev[:, 3] = torch.randint(0, 2, (n,), generator=g).float() * 2 - 1
+        for lvl in range(1, 6):
+            for half in range(2):
+                out["feat2d"][lvl][half][i].normal_(generator=g)
+                out["feat3d"][lvl][half][i].normal_(generator=g)
+            out["efeat2d"][lvl][i].normal_(generator=g)
+            out["flowfeat"][lvl][0][i].normal_(generator=g)
+            out["flowfeat"][lvl][1][i].normal_(generator=g)
+    if pin:
+        out = _map_tensors(out, lambda t: t.pin_memory())
+    return out
+
+
+def _map_tensors(obj, fn):
+    if isinstance(obj, torch.Tensor):
+        return fn(obj)
+    if isinstance(obj, dict):
+        return {k: _map_tensors(v, fn) for k, v in obj.items()}
+    if isinstance(obj, (tuple, list)):
+        return type(obj)(_map_tensors(v, fn) for v in obj)
+    return obj
+
+
+def tensors_nbytes(obj):
+    total = 0
+
+    def add(t):
+        nonlocal total
+        total += t.numel() * t.element_size()
+        return t
+    _map_tensors(obj, add)
+    return total
+
+
+def to_device(host_inputs, device, non_blocking=True):
+    return _map_tensors(host_inputs, lambda t: t.to(device, non_blocking=non_blocking))
+
+
+class _OpTimer:
+    """CUDA-event brackets per op group, recorded on the launching (current) stream."""
+
+    def __init__(self, enabled):
+        self.enabled = enabled
+        self.spans = {}
+
+    def __call__(self, name, fn, *args, **kwargs):
+        if not self.enabled:
+            return fn(*args, **kwargs)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn(*args, **kwargs)
+        b.record()
+        self.spans.setdefault(name, []).append((a, b))
+        return out
+
+    def totals_ms(self):
+        """name -> (total ms, number of brackets); call after a synchronize."""
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.spans.items()}
+
+
+class CostVolumeStack:
+    def __init__(self, cfg, device, seed=0):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        torch.manual_seed(seed)                       # "random-init weights" (BASELINE.json configs[0])
+        self.corr3d = {}
+        for lvl, c in zip(range(1, 6), LEVEL_CHANNELS):
+            mod = pwc3d.Correlation3D(c, c, k=cfg.k)
+            self.corr3d[lvl] = {n: v.to(self.device) for n, v in pwc3d.pack_weights(mod).items()}
+        self._grids = {}
+
+    def pixel_grid(self, batch, h, w):
+        key = (batch, h, w)
+        if key not in self._grids:                    # mesh_grid cache of the reference (models/utils.py:172-183)
+            ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=self.device),
+                                    torch.arange(w, dtype=torch.float32, device=self.device), indexing="ij")
+            self._grids[key] = torch.stack([xs, ys], 0).reshape(1, 2, h * w).expand(batch, 2, h * w).transpose(1, 2).contiguous()
+        return self._grids[key]                       # [B,HW,2] channel-last: what wrapper.py:119-122 produces per call
+
+    def voxelise(self, x):
+        cfg = self.cfg
+        grids = []
+        if cfg.name == "dsec":
+            for i in range(x["ev_x"].shape[0]):
+                grids.append(_events.events_to_voxel_trilinear_device(x["ev_x"][i], x["ev_y"][i], x["ev_t"][i], x["ev_p"][i],
+                                                                       cfg.event_bins, cfg.height, cfg.width, True))
+        else:
+            for i in range(x["events"].shape[0]):
+                grids.append(_events.events_to_voxel_device(x["events"][i], cfg.event_bins, cfg.height, cfg.width, True,
+                                                            check_range=False))
+        return torch.stack(grids)
+
+    @torch.no_grad()
+    def run(self, x, timed=False):
+        """x: device inputs (to_device(make_host_inputs(...))).  Returns (outputs dict, _OpTimer)."""
+        cfg, T = self.cfg, _OpTimer(timed)
+        B = x["pcs"].shape[0]
+        hs, ws = cfg.sensor
+        out = {}
+
+        out["event_voxel"] = T("event_voxel", self.voxelise, x)
+
+        pc1, pc2 = x["pcs"][:, :3].contiguous(), x["pcs"][:, 3:].contiguous()
+        both = torch.cat([pc1, pc2], dim=0).transpose(1, 2).contiguous()                    # pwc3d_core.py:12-13
+        picked = T("fps", ops.furthest_point_sampling, both, max(PYRAMID_POINTS))
+        out["fps_idx"] = picked
+        idx1, idx2 = picked[:B], picked[B:]
+        xyzs1, xyzs2 = [pc1], [pc2]
+        for n in PYRAMID_POINTS:
+            xyzs1.append(T("gather_xyz", projection.batch_indexing_channel_first, pc1, idx1[:, :n]))
+            xyzs2.append(T("gather_xyz", projection.batch_indexing_channel_first, pc2, idx2[:, :n]))
+
+        for lvl in range(5):                                                                 # FeaturePyramid3D, pointconv.py:46
+            for xyzs in (xyzs1, xyzs2):
+                T("knn_pyramid_k16", ops.k_nearest_neighbor, xyzs[lvl], xyzs[lvl + 1], cfg.k)
+
+        out["corr2d"], out["corr3d"], out["proj"], out["sample"], out["knn_self"] = {}, {}, {}, {}, {}
+        for lvl in range(5, 0, -1):
+            c = LEVEL_CHANNELS[lvl - 1]
+            h, w = cfg.level_hw(lvl)
+            xyz1, xyz2 = xyzs1[lvl], xyzs2[lvl]
+            f1_2d, f2_2d = x["feat2d"][lvl][0], x["feat2d"][lvl][1]
+            f1_3d, f2_3d = x["feat3d"][lvl][0], x["feat3d"][lvl][1]
+            ef_2d = x["efeat2d"][lvl]
+            dec_2d, dec_3d = x["flowfeat"][lvl]
+
+            def to_pixels(xyz):                                                              # RPEFlow_core.py:316-324
+                px = (xyz[:, 0:1] + (ws - 1) / 2) * ((w - 1) / (ws - 1))
+                py = (xyz[:, 1:2] + (hs - 1) / 2) * ((h - 1) / (hs - 1))
+                return torch.cat([px, py], dim=1)
+            xy1, xy2 = to_pixels(xyz1), to_pixels(xyz2)
+            grid = self.pixel_grid(B, h, w)
+            nn1 = T("knn_2d_k1", ops.k_nearest_neighbor, xy1.transpose(1, 2).contiguous(), grid, 1)      # :329
+            nn2 = T("knn_2d_k1", ops.k_nearest_neighbor, xy2.transpose(1, 2).contiguous(), grid, 1)      # :330
+            knn11 = T("knn_self_k16", ops.k_nearest_neighbor, xyz1, xyz1, cfg.k)                         # :331
+            out["knn_self"][lvl] = knn11
+
+            p = [T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, f1_2d, f1_3d, nn1[..., 0]),   # :334
+                 T("project_nn_corr", projection.project_feat_with_nn_corr, xy2, f2_2d, f2_3d, nn2[..., 0])]   # :335
+            s = [T("grid_sample", projection.grid_sample_wrapper, f1_2d, xy1),                                # :336
+                 T("grid_sample", projection.grid_sample_wrapper, f2_2d, xy2)]                                # :337
+            if lvl < 5:                                                                       # :354-358 (k=3 searches only)
+                T("knn_interp_k3", ops.k_nearest_neighbor, xyzs1[lvl + 1], xyz1, 3)
+                T("knn_interp_k3", ops.k_nearest_neighbor, xyz1, xyz2, 3)
+
+            knn12 = T("knn_cross_k16", ops.k_nearest_neighbor, xyz2, xyz1, cfg.k)                        # pwc3d_core.py:81
+            cost3d = T("corr3d", pwc3d.correlation3d_forward, xyz1, f1_3d, xyz2, f2_3d, self.corr3d[lvl], knn12, knn11,
+                       cfg.precision)                                                                    # :361
+            cost2d = T("corr2d_L%d" % lvl, ops.correlation2d, f1_2d, f2_2d, cfg.max_displacement)        # :362
+            out["corr3d"][lvl], out["corr2d"][lvl] = cost3d, cost2d
+
+            flow3d_to_2d = xyz1[:, :2]                                                        # stand-in for the 2 flow channels
+            p.append(T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, cost2d,
+                       torch.cat([cost3d, flow3d_to_2d], dim=1), nn1[..., 0]))                           # :373 / :80
+            s.append(T("grid_sample", projection.grid_sample_wrapper,
+                       torch.cat([cost2d, f1_2d[:, :2]], dim=1), xy1))                                   # :376 / :107 (81+2 ch)
+            s.append(T("grid_sample", projection.grid_sample_wrapper, ef_2d, xy1))                       # :108
+            p.append(T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, dec_2d, dec_3d, nn1[..., 0]))   # :394
+            s.append(T("grid_sample", projection.grid_sample_wrapper, dec_2d, xy1))                      # :395
+            out["proj"][lvl], out["sample"][lvl] = p, s
+
+        for i in range(5):                                                                    # :429-430
+            T("knn_interp_k3", ops.k_nearest_neighbor, xyzs1[i + 1], xyzs1[i], 3)
+        return out, T
+
+    @staticmethod
+    def checksum(out):
+        """Small device vector summarising every output: exact int64 sums for index results, fp64 sums for floats."""
+        ints = [out["fps_idx"].sum()] + [out["knn_self"][l].sum() for l in sorted(out["knn_self"])]
+        flts = [out["event_voxel"].double().sum()]
+        for l in sorted(out["corr2d"]):
+            flts += [out["corr2d"][l].double().sum(), out["corr3d"][l].double().sum()]
+            flts += [t.double().sum() for t in out["proj"][l]] + [t.double().sum() for t in out["sample"][l]]
+        return torch.stack(ints).to(torch.float64), torch.stack(flts)
+
+
+# ---- algorithmic work of one frame pair, used by bench.py for the roofline arithmetic ----------------
+def census_work(cfg):
+    hs = {}
+    knn_pairs = 0
+    n_lvls = [cfg.n_points] + PYRAMID_POINTS
+    for lvl in range(5):
+        knn_pairs += 2 * n_lvls[lvl] * n_lvls[lvl + 1]
+    corr2d_bytes, gather_bytes, corr3d_flops = {}, 0, 0
+    for lvl, c in zip(range(1, 6), LEVEL_CHANNELS):
+        h, w = cfg.level_hw(lvl)
+        n = PYRAMID_POINTS[lvl - 1]
+        knn_pairs += 2 * n * h * w + 2 * n * n
+        if lvl < 5:
+            knn_pairs += PYRAMID_POINTS[lvl] * n + n * n
+        corr2d_bytes[lvl] = 4 * h * w * (2 * c + 81)
+        for cc in (c, c, 83, c, 96):
+            gather_bytes += 8 * n + 4 * cc * n + min(16 * cc * n, 4 * cc * h * w)
+        for c2, c3 in ((c, c), (c, c), (81, c + 2), (96, 64)):
+            gather_bytes += h * w * (8 + 4 * c2 + 4 * (c3 + 3)) + 4 * n * (c2 + c3 + 2)
+        corr3d_flops += 2 * n * cfg.k * ((2 * c + 3) * c + c * c) + 4 * n * cfg.k * (24 + 64 + 8 * c) + 4 * n * cfg.k * c
+    for i in range(5):
+        knn_pairs += n_lvls[i + 1] * n_lvls[i]
+    hs["knn_pairs"] = knn_pairs
+    hs["fps_updates"] = 2 * max(PYRAMID_POINTS) * cfg.n_points
+    hs["corr2d_bytes"] = corr2d_bytes
+    hs["gather_bytes"] = gather_bytes
+    hs["corr3d_flops"] = corr3d_flops
+    hs["event_voxel_bytes"] = 16 * cfg.n_events + 4 * 2 * cfg.event_bins * cfg.height * cfg.width
+    return hs

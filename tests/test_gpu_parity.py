@@ -286,8 +286,11 @@ def test_grid_sample_golden_and_levels(golden):
         want = spec.grid_sample_pts(feat.numpy(), xy.numpy())
         got = b200.grid_sample_wrapper(feat.to(DEV), xy.to(DEV))
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
-        lib_ref = torch_ref.grid_sample_wrapper(feat.to(DEV), xy.to(DEV))                    # ATen's CUDA grid_sampler
-        torch.testing.assert_close(got, lib_ref, rtol=1e-5, atol=1e-5)
+        # ATen's CUDA path: the same torch ops on the GPU divide by the python scalar (W-1) as x * (1/(W-1)), so the
+        # pixel coordinate differs from the CPU reference (true division, = our rule) by 1-2 ulp(|x|) ~ 3e-5 px;
+        # times the feature gradient that is ~1e-4 absolute.  Looser bar, cross-check only.
+        lib_ref = torch_ref.grid_sample_wrapper(feat.to(DEV), xy.to(DEV))
+        torch.testing.assert_close(got, lib_ref, rtol=1e-4, atol=5e-4)
 
 
 def test_project_nn_corr_golden_and_levels(golden):
