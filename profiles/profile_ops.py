@@ -1,0 +1,63 @@
+"""Run each hot-path kernel once at its dominant shape (cfg1 level 1, batch 32) between cudaProfilerStart/Stop,
+so `ncu --profile-from-start off` captures exactly one launch per kernel:
+
+  ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/ops python profiles/profile_ops.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import rpeflow_b200 as b200  # noqa: E402
+from rpeflow_b200 import events, ops, pwc3d  # noqa: E402
+
+dev = torch.device("cuda", 0)
+B = int(os.environ.get("PROFILE_BATCH", "32"))
+g = torch.Generator().manual_seed(0)
+C, H, W, N = 32, 144, 240, 4096
+f1 = torch.randn(B, H, W, C, generator=g).to(dev)
+f2 = torch.randn(B, H, W, C, generator=g).to(dev)
+pc = torch.rand(2 * B, 8192, 3, generator=g).to(dev)
+xyz = torch.rand(B, N, 3, generator=g).to(dev)
+xyz_big = torch.rand(B, 8192, 3, generator=g).to(dev)
+xy = (torch.rand(B, N, 2, generator=g) * torch.tensor([W - 1.0, H - 1.0])).to(dev)
+ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+grid = torch.stack([xs, ys], -1).reshape(1, H * W, 2).expand(B, H * W, 2).contiguous().to(dev)
+feat2d = torch.randn(B, C, H, W, generator=g).to(dev)
+feat96 = torch.randn(B, 96, H, W, generator=g).to(dev)
+feat3d = torch.randn(B, C, N, generator=g).to(dev)
+ev = torch.zeros(1_000_000, 4)
+ev[:, 0] = torch.randint(0, 960, (1_000_000,), generator=g).float()
+ev[:, 1] = torch.randint(0, 540, (1_000_000,), generator=g).float()
+ev[:, 2] = torch.sort(torch.rand(1_000_000, generator=g)).values
+ev[:, 3] = torch.randint(0, 2, (1_000_000,), generator=g).float() * 2 - 1
+ev = ev.to(dev)
+torch.manual_seed(0)
+wts = {n: v.to(dev) for n, v in pwc3d.pack_weights(pwc3d.Correlation3D(C, C)).items()}
+xyz_cf = xyz.transpose(1, 2).contiguous()
+xy_cf = xy.transpose(1, 2).contiguous()
+
+
+def once():
+    ops._correlation_forward_cuda(f1, f2, 4)
+    ops._furthest_point_sampling_cuda(pc, 4096)
+    ops._k_nearest_neighbor_cuda(xyz_big, xyz, 16)             # pyramid 8192 -> 4096
+    knn11 = ops._k_nearest_neighbor_cuda(xyz, xyz, 16)         # self, level 1
+    ops._k_nearest_neighbor_cuda(xyz, xyz, 3)                  # interpolation searches
+    nn = ops._k_nearest_neighbor_cuda(xy, grid, 1)             # pixel grid -> projected points
+    pwc3d.correlation3d_forward(xyz_cf, feat3d, xyz_cf, feat3d, wts, knn11, knn11)
+    b200.grid_sample_wrapper(feat96, xy_cf)
+    b200.project_feat_with_nn_corr(xy_cf, feat2d, feat3d, nn[..., 0])
+    b200.batch_indexing_channel_first(feat3d, knn11)
+    events.events_to_voxel_device(ev, 10, 540, 960, True, check_range=False)
+
+
+for _ in range(2):
+    once()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+once()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("profiled one launch of every hot-path kernel at level-1 shapes, batch", B)
