@@ -64,6 +64,44 @@ __device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
 }
 
+
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2): two independent fp32 lanes per instruction ----
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// a*a rounded ONCE.  ptxas (CUDA 12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false,
+// which would break the non-fused distance rule; fma(a, a, -0.0) with the -0.0 coming from a kernel argument is a
+// correctly rounded product that leaves nothing to contract.
+__device__ __forceinline__ u64 sqr2(u64 a, u64 negzero2) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(a), "l"(negzero2));
+    return r;
+}
+// The distance rule on two (a,b) pairs at once: ((dx*dx + dy*dy) + dz*dz), each step rounded separately.
+template <int D>
+__device__ __forceinline__ u64 sqdist_pair(u64 ax, u64 ay, u64 az, u64 bx, u64 by, u64 bz, u64 nz) {
+    const u64 xx = sqr2(sub2(ax, bx), nz), yy = sqr2(sub2(ay, by), nz);
+    u64 s = add2(xx, yy);
+    if (D == 3) s = add2(s, sqr2(sub2(az, bz), nz));
+    return s;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
     unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
     int bytes = valid ? 16 : 0;   // src-size 0 -> the 16 destination bytes are zero-filled

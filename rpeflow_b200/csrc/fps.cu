@@ -33,7 +33,7 @@ struct FpsSlot {               // what a CTA publishes to its cluster peers each
 
 template <int PPT, int T, int CS>
 __global__ void __launch_bounds__(T, 1)
-fps_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int N, int S) {
+fps_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int N, int S, float negzero) {
     constexpr int NW = T / 32;
     __shared__ unsigned s_d[2][32], s_i[2][32];
     __shared__ __align__(16) FpsSlot s_slot[2][CS > 1 ? CS : 1];
@@ -74,15 +74,32 @@ fps_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int N, int 
         if (rank == 0 && tid == 0) o[s] = (int64_t)cur;
         if (s == S - 1) break;
 
+        // Running argmax over this thread's points.  Only the slot number is tracked in the loop (SEL with an
+        // immediate); padding slots hold distance 0 and an index >= hi, so they lose every tie to a real point.
         float bd = -1.0f;
-        unsigned bi = 0xFFFFFFFFu;
+        int bslot = 0;
+        if (PPT >= 2) {                                  // two points per FADD2/FFMA2 (non-fused rule kept, see sqr2)
+            const u64 nz = pack2(negzero, negzero);
+            const u64 c2x = pack2(cx, cx), c2y = pack2(cy, cy), c2z = pack2(cz, cz);
 #pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-            const float d = sqdist3_rule(px[i], py[i], pz[i], cx, cy, cz);
-            dist[i] = fminf(dist[i], d);
-            const unsigned gi = (unsigned)(lo + i * T + tid);
-            if (dist[i] > bd) { bd = dist[i]; bi = gi < (unsigned)hi ? gi : 0xFFFFFFFFu; }   // increasing index, strict '>'
+            for (int i = 0; i + 1 < PPT; i += 2) {
+                float d0, d1;
+                unpack2(sqdist_pair<3>(pack2(px[i], px[i + 1]), pack2(py[i], py[i + 1]), pack2(pz[i], pz[i + 1]),
+                                       c2x, c2y, c2z, nz), d0, d1);
+                dist[i] = fminf(dist[i], d0);
+                dist[i + 1] = fminf(dist[i + 1], d1);
+                if (dist[i] > bd) { bd = dist[i]; bslot = i; }                  // increasing index, strict '>': lowest index wins
+                if (dist[i + 1] > bd) { bd = dist[i + 1]; bslot = i + 1; }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PPT; ++i) {
+                const float d = sqdist3_rule(px[i], py[i], pz[i], cx, cy, cz);
+                dist[i] = fminf(dist[i], d);
+                if (dist[i] > bd) { bd = dist[i]; bslot = i; }
+            }
         }
+        const unsigned bi = (unsigned)(lo + bslot * T + tid);
         const unsigned db = __float_as_uint(bd);         // distances are >= +0: the bit pattern orders like the value
         const unsigned wmax = __reduce_max_sync(FULL, db);
         const unsigned widx = __reduce_min_sync(FULL, db == wmax ? bi : 0xFFFFFFFFu);
@@ -108,7 +125,7 @@ fps_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int N, int 
                 if (lane < CS) {                         // lane r writes this CTA's winner into peer r's slot
                     FpsSlot v;
                     v.key = ((unsigned long long)gmax << 32) | (unsigned long long)(0xFFFFFFFFu - gidx);
-                    const int li = gidx != 0xFFFFFFFFu ? (int)gidx - lo : 0;
+                    const int li = (int)gidx - lo;          // < PPT*T even for a padding slot (never the global winner)
                     v.x = s_pts[li * 3 + 0]; v.y = s_pts[li * 3 + 1]; v.z = s_pts[li * 3 + 2]; v.pad = 0.0f;
                     FpsSlot* dst = cluster.map_shared_rank(&s_slot[par][rank], lane);
                     *dst = v;
@@ -132,7 +149,7 @@ template <int PPT, int T, int CS>
 static cudaError_t launch_fps(const float* xyz, int64_t* idx, int B, int N, int S, cudaStream_t st) {
     auto kern = fps_kernel<PPT, T, CS>;
     if (CS == 1) {
-        kern<<<B, T, 0, st>>>(xyz, idx, N, S);
+        kern<<<B, T, 0, st>>>(xyz, idx, N, S, -0.0f);
         return cudaGetLastError();
     }
     const size_t smem = (size_t)PPT * T * 3 * sizeof(float);
@@ -150,7 +167,7 @@ static cudaError_t launch_fps(const float* xyz, int64_t* idx, int B, int N, int 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, xyz, idx, N, S);
+    return cudaLaunchKernelEx(&cfg, kern, xyz, idx, N, S, -0.0f);
 }
 
 template <int CS>
