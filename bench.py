@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--cpu-sample-s", type=float, default=20.0, help="target seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--eager", action="store_true", help="no CUDA graphs: launch every kernel from Python (debugging)")
     return ap.parse_args()
 
 
@@ -259,24 +259,34 @@ def main():
     x = to_device(host, dev)
     torch.cuda.synchronize()
 
-    # -------- device-resident timing: W warm-up + exactly K timed steps, CUDA events on the launching stream
+    # -------- device-resident timing: W warm-up + exactly K timed steps, CUDA events on the launching stream.
+    # A step = one replay of the CUDA graph of CostVolumeStack.run (every kernel of the census, two-stream overlap
+    # of the point chain with the point-independent 2-D ops); --eager launches the same kernels from Python.
+    from rpeflow_b200.stack import GraphedStack, HostFeeder
+    if args.eager:
+        step_fn = lambda: stack.run(x, overlap=True)
+        l0 = _lib.LAUNCHES
+        step_fn()
+        launches_per_step = _lib.LAUNCHES - l0
+    else:
+        l0 = _lib.LAUNCHES
+        graphed = GraphedStack(stack, x, fused=True, with_checksum=False)
+        launches_per_step = (_lib.LAUNCHES - l0) // 2          # one eager warm-up + one capture
+        step_fn = graphed.replay
     for _ in range(max(3, args.warmup)):
-        stack.run(x)
+        step_fn()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = _lib.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    timers = []
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        _, T = stack.run(x, timed=True)
-        timers.append(T)
+        step_fn()
     ev1.record()
     barrier()
     clocks = sampler.finish()
-    launches = _lib.LAUNCHES - launches0
+    launches = launches_per_step * args.steps
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -284,14 +294,21 @@ def main():
     ms_step = float(t.item()) / args.steps
     value = world * B / (ms_step * 1e-3)
 
-    # per-op device time (rank 0), averaged over the timed steps
+    # per-op device time (rank 0): a separate serial, eager pass with CUDA-event brackets around every op
+    timers = []
+    stack.run(x)                                        # allocator warm-up outside the brackets
+    torch.cuda.synchronize()
+    for _ in range(3):
+        _, T = stack.run(x, timed=True)
+        timers.append(T)
+    torch.cuda.synchronize()
     per_op = {}
     for T in timers:
         for name, (ms, n) in T.totals_ms().items():
             acc = per_op.setdefault(name, [0.0, 0])
             acc[0] += ms
             acc[1] += n
-    per_op = {k: {"ms_per_step": v[0] / args.steps, "calls_per_step": v[1] // args.steps} for k, v in per_op.items()}
+    per_op = {k: {"ms_per_step": v[0] / len(timers), "calls_per_step": v[1] // len(timers)} for k, v in per_op.items()}
 
     # -------- roofline of the dominant HBM-bound kernel: corr2d at pyramid level 1
     work = census_work(cfg)
@@ -340,51 +357,57 @@ def main():
         "corr3d_tflops_dense_equiv": work["corr3d_flops"] * B / (1e-3 * per_op["corr3d"]["ms_per_step"]) / 1e12,
     }
 
-    # -------- end to end: host (pinned) -> device copies of every step input + device -> host read of the result
+    # -------- end to end: every step copies ALL of its inputs from pinned host memory (copy stream, group by group
+    # in dependency order) into one of two device input sets, replays the per-group CUDA graphs as the groups land,
+    # and reads the step's checksum vector back to the host.  Step s+1's copies overlap step s's compute.
     e2e = None
     if not args.no_e2e:
-        chunks = max(1, min(args.e2e_chunks, B))
-        while B % chunks:
-            chunks -= 1
-        cb = B // chunks
+        if not args.eager:
+            del graphed
+        feeder = HostFeeder(host, dev, depth=2)
+        if args.eager:
+            class _Eager:
+                def __init__(self, xs):
+                    self.xs = xs
 
-        def slice_inputs(obj, lo, hi):
-            from rpeflow_b200.stack import _map_tensors
+                def replay(self, wait=None):
+                    out, _ = stack.run(self.xs, wait=wait)
+                    self.checksum = stack.checksum(out)
+            runners = [_Eager(sl) for sl in feeder.slots]
+        else:
+            runners = [GraphedStack(stack, sl, fused=False) for sl in feeder.slots]
+        result_host = torch.zeros((2, 2, 64), dtype=torch.float64).pin_memory()
+        main_stream = torch.cuda.current_stream()
+        consumed = []
 
-            return _map_tensors(obj, lambda tt: tt[lo:hi])        # batch is dim 0 of every input tensor
-        host_chunks = [slice_inputs(host, i * cb, (i + 1) * cb) for i in range(chunks)]
-        h2d_bytes = sum(tensors_nbytes(hc) for hc in host_chunks)
-        copy_stream = torch.cuda.Stream(device=dev)
-        result_host = torch.empty((chunks, 2, 64), dtype=torch.float64).pin_memory()
-
-        def e2e_step():
-            staged = []
-            for i in range(chunks):                     # copies run ahead on their own stream, compute follows chunk by chunk
-                with torch.cuda.stream(copy_stream):
-                    # strided host views (batch slices) are copied tensor by tensor from pinned memory
-                    xi = to_device(host_chunks[i], dev, non_blocking=True)
-                    done = torch.cuda.Event()
-                    done.record(copy_stream)
-                staged.append((xi, done))
-            for i, (xi, done) in enumerate(staged):
-                torch.cuda.current_stream().wait_event(done)
-                out, _ = stack.run(xi)
-                ints, flts = stack.checksum(out)
-                result_host[i, 0, :ints.numel()].copy_(ints, non_blocking=True)
-                result_host[i, 1, :flts.numel()].copy_(flts, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return out
-        d2h_bytes = 0
-        for _ in range(2):
-            o = e2e_step()
-        ints, flts = stack.checksum(o)
-        d2h_bytes = chunks * 8 * (ints.numel() + flts.numel())
+        def e2e_run(steps):
+            done = [None, None]
+            pending = feeder.issue(0)
+            for s in range(steps):
+                slot = s % 2
+                evs = pending
+                if s + 1 < steps:                       # next step's copies start as soon as its device set is free
+                    pending = feeder.issue((s + 1) % 2, after=done[(s + 1) % 2])
+                runners[slot].replay(wait=lambda g, evs=evs: main_stream.wait_event(evs[g]))
+                ints, flts = runners[slot].checksum
+                result_host[slot, 0, :ints.numel()].copy_(ints, non_blocking=True)
+                result_host[slot, 1, :flts.numel()].copy_(flts, non_blocking=True)
+                d = torch.cuda.Event()
+                d.record(main_stream)
+                done[slot] = d
+                if s >= 1:                              # the host reads step s-1's result while step s runs
+                    done[(s - 1) % 2].synchronize()
+                    consumed.append(float(result_host[(s - 1) % 2, 1, 0]))
+            main_stream.synchronize()
+            consumed.append(float(result_host[(steps - 1) % 2, 1, 0]))
+            return ints.numel() + flts.numel()
+        nres = e2e_run(2)
+        d2h_bytes = 8 * nres
         barrier()
         w0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_run(args.steps)
         e1.record()
         barrier()
         wall = time.perf_counter() - w0
@@ -392,9 +415,13 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * args.steps / float(te.item()), "unit": "frame-pairs/s",
-               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "chunks": chunks,
+               "h2d_bytes_per_step": feeder.nbytes, "d2h_bytes_per_step": d2h_bytes,
+               "h2d_gbs": feeder.nbytes * args.steps / float(te.item()) / 1e9,
+               "pipeline": "2 device input sets; copies of step s+1 (copy stream, 7 groups in dependency order) overlap the "
+                           "graph replays of step s; result read back every step",
                "inputs_copied": "point clouds, raw events and every synthetic activation the ops read",
                "wall_s": wall}
+        del runners, feeder
 
     # -------- cross-rank verification (NCCL all-gather of checksums of one common sample)
     verify = None

@@ -20,11 +20,21 @@ def _dev(device):
     return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
 
-def events_to_voxel_device(events, num_bins, height, width, event_polarity, check_range=True):
-    """events: CUDA fp32 [n,4] (x,y,t,p), time-sorted -> CUDA fp32 [bins*(2|1),H,W]."""
+def _grid(out, num_bins, height, width, event_polarity, device):
+    shape = (num_bins * (2 if event_polarity else 1), height, width)
+    if out is None:
+        return torch.empty(shape, dtype=torch.float32, device=device)
+    if tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+        raise RuntimeError(f"out must be a contiguous CUDA fp32 tensor of shape {shape}")
+    return out
+
+
+def events_to_voxel_device(events, num_bins, height, width, event_polarity, check_range=True, out=None):
+    """events: CUDA fp32 [n,4] (x,y,t,p), time-sorted -> CUDA fp32 [bins*(2|1),H,W] (written into `out` if given,
+    e.g. one sample's slice of a batched grid)."""
     ev = events.contiguous().float()
     n = ev.shape[0]
-    vox = torch.empty((num_bins * (2 if event_polarity else 1), height, width), dtype=torch.float32, device=ev.device)
+    vox = _grid(out, num_bins, height, width, event_polarity, ev.device)
     status = torch.empty((1,), dtype=torch.int32, device=ev.device)
     with torch.cuda.device(ev.device):
         check(lib.b200_event_voxel_int(ev.data_ptr(), n, vox.data_ptr(), int(num_bins), int(height), int(width),
@@ -50,12 +60,12 @@ def eventsToVoxel(events, num_bins=5, height=None, width=None, event_polarity=Fa
     return events_to_voxel_device(ev, num_bins, height, width, event_polarity).cpu().numpy()
 
 
-def events_to_voxel_trilinear_device(x, y, t, p, num_bins, height, width, event_polarity):
+def events_to_voxel_trilinear_device(x, y, t, p, num_bins, height, width, event_polarity, out=None):
     """x,y,p: CUDA fp32 [n]; t: CUDA int64 [n] (sorted) -> CUDA fp32 [bins*(2|1),H,W]."""
     x, y, p = (a.contiguous().float() for a in (x, y, p))
     t = t.contiguous().to(torch.int64)
     n = x.shape[0]
-    vox = torch.empty((num_bins * (2 if event_polarity else 1), height, width), dtype=torch.float32, device=x.device)
+    vox = _grid(out, num_bins, height, width, event_polarity, x.device)
     scratch = torch.empty((8,), dtype=torch.int32, device=x.device)
     with torch.cuda.device(x.device):
         check(lib.b200_event_voxel_trilinear(x.data_ptr(), y.data_ptr(), t.data_ptr(), p.data_ptr(), n, vox.data_ptr(),

@@ -192,50 +192,46 @@ class CostVolumeStack:
 
     def voxelise(self, x):
         cfg = self.cfg
-        grids = []
-        if cfg.name == "dsec":
-            for i in range(x["ev_x"].shape[0]):
-                grids.append(_events.events_to_voxel_trilinear_device(x["ev_x"][i], x["ev_y"][i], x["ev_t"][i], x["ev_p"][i],
-                                                                       cfg.event_bins, cfg.height, cfg.width, True))
-        else:
-            for i in range(x["events"].shape[0]):
-                grids.append(_events.events_to_voxel_device(x["events"][i], cfg.event_bins, cfg.height, cfg.width, True,
-                                                            check_range=False))
-        return torch.stack(grids)
+        nb = x["ev_x"].shape[0] if cfg.name == "dsec" else x["events"].shape[0]
+        grids = torch.empty((nb, 2 * cfg.event_bins, cfg.height, cfg.width), dtype=torch.float32, device=self.device)
+        for i in range(nb):                          # the reference voxelises sample by sample (dataset __getitem__)
+            if cfg.name == "dsec":
+                _events.events_to_voxel_trilinear_device(x["ev_x"][i], x["ev_y"][i], x["ev_t"][i], x["ev_p"][i],
+                                                         cfg.event_bins, cfg.height, cfg.width, True, out=grids[i])
+            else:
+                _events.events_to_voxel_device(x["events"][i], cfg.event_bins, cfg.height, cfg.width, True,
+                                               check_range=False, out=grids[i])
+        return grids
 
-    @torch.no_grad()
-    def run(self, x, timed=False):
-        """x: device inputs (to_device(make_host_inputs(...))).  Returns (outputs dict, _OpTimer)."""
-        cfg, T = self.cfg, _OpTimer(timed)
+    # ---- the census, split into stages by the input group each one needs -------------------------------------
+    #   "points" : point clouds + per-point features  -> FPS, pyramid gathers, all 43 KNN searches, 5 Correlation3D
+    #   "events" : raw events                         -> voxel grid
+    #   "lvl<l>" : the 2-D activations of level l      -> correlation2d, projections, samplers of that level
+    # Ops inside a stage keep the reference's call order; stages only depend on "points" (and on their own group),
+    # so a feeder can stream the big 2-D activations in while the point work is already running.
+    def _stage_points(self, x, S, T):
+        cfg = self.cfg
         B = x["pcs"].shape[0]
         hs, ws = cfg.sensor
-        out = {}
-
-        out["event_voxel"] = T("event_voxel", self.voxelise, x)
-
         pc1, pc2 = x["pcs"][:, :3].contiguous(), x["pcs"][:, 3:].contiguous()
         both = torch.cat([pc1, pc2], dim=0).transpose(1, 2).contiguous()                    # pwc3d_core.py:12-13
         picked = T("fps", ops.furthest_point_sampling, both, max(PYRAMID_POINTS))
-        out["fps_idx"] = picked
+        S["out"]["fps_idx"] = picked
         idx1, idx2 = picked[:B], picked[B:]
         xyzs1, xyzs2 = [pc1], [pc2]
         for n in PYRAMID_POINTS:
             xyzs1.append(T("gather_xyz", projection.batch_indexing_channel_first, pc1, idx1[:, :n]))
             xyzs2.append(T("gather_xyz", projection.batch_indexing_channel_first, pc2, idx2[:, :n]))
+        S["xyzs1"], S["xyzs2"] = xyzs1, xyzs2
 
         for lvl in range(5):                                                                 # FeaturePyramid3D, pointconv.py:46
             for xyzs in (xyzs1, xyzs2):
                 T("knn_pyramid_k16", ops.k_nearest_neighbor, xyzs[lvl], xyzs[lvl + 1], cfg.k)
 
-        out["corr2d"], out["corr3d"], out["proj"], out["sample"], out["knn_self"] = {}, {}, {}, {}, {}
         for lvl in range(5, 0, -1):
-            c = LEVEL_CHANNELS[lvl - 1]
             h, w = cfg.level_hw(lvl)
             xyz1, xyz2 = xyzs1[lvl], xyzs2[lvl]
-            f1_2d, f2_2d = x["feat2d"][lvl][0], x["feat2d"][lvl][1]
             f1_3d, f2_3d = x["feat3d"][lvl][0], x["feat3d"][lvl][1]
-            ef_2d = x["efeat2d"][lvl]
-            dec_2d, dec_3d = x["flowfeat"][lvl]
 
             def to_pixels(xyz):                                                              # RPEFlow_core.py:316-324
                 px = (xyz[:, 0:1] + (ws - 1) / 2) * ((w - 1) / (ws - 1))
@@ -246,35 +242,99 @@ class CostVolumeStack:
             nn1 = T("knn_2d_k1", ops.k_nearest_neighbor, xy1.transpose(1, 2).contiguous(), grid, 1)      # :329
             nn2 = T("knn_2d_k1", ops.k_nearest_neighbor, xy2.transpose(1, 2).contiguous(), grid, 1)      # :330
             knn11 = T("knn_self_k16", ops.k_nearest_neighbor, xyz1, xyz1, cfg.k)                         # :331
-            out["knn_self"][lvl] = knn11
-
-            p = [T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, f1_2d, f1_3d, nn1[..., 0]),   # :334
-                 T("project_nn_corr", projection.project_feat_with_nn_corr, xy2, f2_2d, f2_3d, nn2[..., 0])]   # :335
-            s = [T("grid_sample", projection.grid_sample_wrapper, f1_2d, xy1),                                # :336
-                 T("grid_sample", projection.grid_sample_wrapper, f2_2d, xy2)]                                # :337
+            S["out"]["knn_self"][lvl] = knn11
             if lvl < 5:                                                                       # :354-358 (k=3 searches only)
                 T("knn_interp_k3", ops.k_nearest_neighbor, xyzs1[lvl + 1], xyz1, 3)
                 T("knn_interp_k3", ops.k_nearest_neighbor, xyz1, xyz2, 3)
-
             knn12 = T("knn_cross_k16", ops.k_nearest_neighbor, xyz2, xyz1, cfg.k)                        # pwc3d_core.py:81
             cost3d = T("corr3d", pwc3d.correlation3d_forward, xyz1, f1_3d, xyz2, f2_3d, self.corr3d[lvl], knn12, knn11,
                        cfg.precision)                                                                    # :361
-            cost2d = T("corr2d_L%d" % lvl, ops.correlation2d, f1_2d, f2_2d, cfg.max_displacement)        # :362
-            out["corr3d"][lvl], out["corr2d"][lvl] = cost3d, cost2d
-
-            flow3d_to_2d = xyz1[:, :2]                                                        # stand-in for the 2 flow channels
-            p.append(T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, cost2d,
-                       torch.cat([cost3d, flow3d_to_2d], dim=1), nn1[..., 0]))                           # :373 / :80
-            s.append(T("grid_sample", projection.grid_sample_wrapper,
-                       torch.cat([cost2d, f1_2d[:, :2]], dim=1), xy1))                                   # :376 / :107 (81+2 ch)
-            s.append(T("grid_sample", projection.grid_sample_wrapper, ef_2d, xy1))                       # :108
-            p.append(T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, dec_2d, dec_3d, nn1[..., 0]))   # :394
-            s.append(T("grid_sample", projection.grid_sample_wrapper, dec_2d, xy1))                      # :395
-            out["proj"][lvl], out["sample"][lvl] = p, s
+            S["out"]["corr3d"][lvl] = cost3d
+            S[lvl] = {"xy1": xy1, "xy2": xy2, "nn1": nn1[..., 0], "nn2": nn2[..., 0]}
 
         for i in range(5):                                                                    # :429-430
             T("knn_interp_k3", ops.k_nearest_neighbor, xyzs1[i + 1], xyzs1[i], 3)
-        return out, T
+
+    def _stage_events(self, x, S, T):
+        S["out"]["event_voxel"] = T("event_voxel", self.voxelise, x)
+
+    def _stage_corr2d(self, x, S, T, lvl):
+        f1_2d, f2_2d = x["feat2d"][lvl]
+        S["out"]["corr2d"][lvl] = T("corr2d_L%d" % lvl, ops.correlation2d, f1_2d, f2_2d, self.cfg.max_displacement)   # :362
+
+    def _stage_level(self, x, S, T, lvl):
+        L = S[lvl]
+        xy1, xy2, nn1, nn2 = L["xy1"], L["xy2"], L["nn1"], L["nn2"]
+        xyz1 = S["xyzs1"][lvl]
+        f1_2d, f2_2d = x["feat2d"][lvl]
+        f1_3d, f2_3d = x["feat3d"][lvl]
+        ef_2d = x["efeat2d"][lvl]
+        dec_2d, dec_3d = x["flowfeat"][lvl]
+        cost2d, cost3d = S["out"]["corr2d"][lvl], S["out"]["corr3d"][lvl]
+        p = [T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, f1_2d, f1_3d, nn1),            # :334
+             T("project_nn_corr", projection.project_feat_with_nn_corr, xy2, f2_2d, f2_3d, nn2)]            # :335
+        s = [T("grid_sample", projection.grid_sample_wrapper, f1_2d, xy1),                                  # :336
+             T("grid_sample", projection.grid_sample_wrapper, f2_2d, xy2)]                                  # :337
+        flow3d_to_2d = xyz1[:, :2]                                                            # stand-in for the 2 flow channels
+        p.append(T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, cost2d,
+                   torch.cat([cost3d, flow3d_to_2d], dim=1), nn1))                                         # :373 / :80
+        s.append(T("grid_sample", projection.grid_sample_wrapper,
+                   torch.cat([cost2d, f1_2d[:, :2]], dim=1), xy1))                                         # :376 / :107 (81+2 ch)
+        s.append(T("grid_sample", projection.grid_sample_wrapper, ef_2d, xy1))                             # :108
+        p.append(T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, dec_2d, dec_3d, nn1))     # :394
+        s.append(T("grid_sample", projection.grid_sample_wrapper, dec_2d, xy1))                            # :395
+        S["out"]["proj"][lvl], S["out"]["sample"][lvl] = p, s
+
+    @staticmethod
+    def _new_state():
+        return {"out": {"corr2d": {}, "corr3d": {}, "proj": {}, "sample": {}, "knn_self": {}}}
+
+    def segments(self):
+        """[(input group, fn(x, S, T))] in execution order."""
+        segs = [("points", self._stage_points), ("events", self._stage_events)]
+        for lvl in range(5, 0, -1):
+            def level(x, S, T, lvl=lvl):
+                self._stage_corr2d(x, S, T, lvl)
+                self._stage_level(x, S, T, lvl)
+            segs.append(("lvl%d" % lvl, level))
+        return segs
+
+    @torch.no_grad()
+    def run(self, x, timed=False, wait=None, overlap=False):
+        """x: device inputs (to_device(make_host_inputs(...))).  Returns (outputs dict, _OpTimer).
+
+        wait(group): called before the first op that reads input group `group` (a feeder makes the current stream
+        wait for that group's host->device copy there).  overlap=True runs the ops that need no point data (voxel
+        grid, the five correlation2d) on a second stream next to the FPS/KNN chain, which is a 64-CTA latency chain
+        and leaves most SMs idle."""
+        T = _OpTimer(timed)
+        S = self._new_state()
+        wait = wait or (lambda group: None)
+        if overlap and not timed:
+            main = torch.cuda.current_stream(self.device)
+            side = self._side_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                wait("events")
+                self._stage_events(x, S, T)
+                for lvl in range(5, 0, -1):
+                    wait("lvl%d" % lvl)
+                    self._stage_corr2d(x, S, T, lvl)
+            wait("points")
+            self._stage_points(x, S, T)
+            main.wait_stream(side)
+            for lvl in range(5, 0, -1):
+                self._stage_level(x, S, T, lvl)
+        else:
+            for group, fn in self.segments():
+                wait(group)
+                fn(x, S, T)
+        return S["out"], T
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     @staticmethod
     def checksum(out):
@@ -285,6 +345,101 @@ class CostVolumeStack:
             flts += [out["corr2d"][l].double().sum(), out["corr3d"][l].double().sum()]
             flts += [t.double().sum() for t in out["proj"][l]] + [t.double().sum() for t in out["sample"][l]]
         return torch.stack(ints).to(torch.float64), torch.stack(flts)
+
+
+INPUT_GROUPS = ["points", "events", "lvl5", "lvl4", "lvl3", "lvl2", "lvl1"]      # host->device copy order of a feeder
+
+
+def group_tensors(x):
+    """{group: [tensors]} for an input tree (host or device), in the order a feeder copies them."""
+    g = {name: [] for name in INPUT_GROUPS}
+    g["points"].append(x["pcs"])
+    for lvl in range(5, 0, -1):
+        g["points"] += [x["feat3d"][lvl][0], x["feat3d"][lvl][1], x["flowfeat"][lvl][1]]
+        g["lvl%d" % lvl] += [x["feat2d"][lvl][0], x["feat2d"][lvl][1], x["efeat2d"][lvl], x["flowfeat"][lvl][0]]
+    g["events"] += [x[k] for k in ("events", "ev_x", "ev_y", "ev_t", "ev_p") if k in x]
+    return g
+
+
+class HostFeeder:
+    """Streams one step's inputs from pinned host memory into one of `depth` preallocated device input sets on a
+    copy stream, group by group in dependency order (small point data first, the level-1 activations last), and
+    records one event per group so the compute stream only waits for what the next stage reads."""
+
+    def __init__(self, host, device, depth=2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [_map_tensors(host, lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device))
+                      for _ in range(depth)]
+        src = group_tensors(host)
+        self.plan = []
+        for slot in self.slots:
+            dst = group_tensors(slot)
+            self.plan.append([(name, list(zip(dst[name], src[name]))) for name in INPUT_GROUPS])
+        self.nbytes = tensors_nbytes(host)
+
+    def issue(self, slot, after=None):
+        """Enqueue the copies into device set `slot` (after event `after`, e.g. the last compute that read that
+        set).  Returns {group: event}."""
+        events = {}
+        with torch.cuda.stream(self.stream):
+            if after is not None:
+                self.stream.wait_event(after)
+            for name, pairs in self.plan[slot]:
+                for dst, src in pairs:
+                    dst.copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                events[name] = ev
+        return events
+
+
+class GraphedStack:
+    """CUDA-graph capture of CostVolumeStack over a fixed device input set: the ~900 launches of a step become one
+    graph replay (fused=True: a single graph with the two-stream overlap of CostVolumeStack.run) or one replay per
+    input group (fused=False: a feeder's copy events are waited on between replays).  Outputs are static tensors
+    owned by the graphs' memory pool."""
+
+    def __init__(self, stack, x, fused=True, with_checksum=True):
+        self.stack, self.x, self.fused = stack, x, fused
+        self.graphs = []
+        self.out = None
+        self.checksum = None
+        warm = torch.cuda.Stream(device=stack.device)
+        warm.wait_stream(torch.cuda.current_stream(stack.device))
+        with torch.cuda.stream(warm):                 # eager warm-up: allocator, pixel-grid cache, function attributes
+            stack.run(x, overlap=fused)
+        torch.cuda.current_stream(stack.device).wait_stream(warm)
+        torch.cuda.synchronize(stack.device)
+        pool = torch.cuda.graph_pool_handle()
+        T = _OpTimer(False)
+        with torch.no_grad():
+            if fused:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    self.out, _ = stack.run(x, overlap=True)
+                    if with_checksum:
+                        self.checksum = stack.checksum(self.out)
+                self.graphs.append((None, g))
+            else:
+                S = stack._new_state()
+                segs = stack.segments()
+                for n, (group, fn) in enumerate(segs):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):
+                        fn(x, S, T)
+                        if with_checksum and n == len(segs) - 1:
+                            self.checksum = stack.checksum(S["out"])
+                    self.graphs.append((group, g))
+                self._state = S                       # keeps every intermediate tensor of the pool alive
+                self.out = S["out"]
+
+    def replay(self, wait=None):
+        for group, g in self.graphs:
+            if wait is not None and group is not None:
+                wait(group)
+            g.replay()
+        return self.out
 
 
 # ---- algorithmic work of one frame pair (SURVEY §8d), used by bench.py for the roofline arithmetic ----------------
