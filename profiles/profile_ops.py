@@ -39,8 +39,13 @@ xyz_cf = xyz.transpose(1, 2).contiguous()
 xy_cf = xy.transpose(1, 2).contiguous()
 
 
+ONLY = os.environ.get("PROFILE_ONLY", "")
+
+
 def once():
     ops._correlation_forward_cuda(f1, f2, 4)
+    if ONLY == "corr2d":
+        return
     ops._furthest_point_sampling_cuda(pc, 4096)
     ops._k_nearest_neighbor_cuda(xyz_big, xyz, 16)             # pyramid 8192 -> 4096
     knn11 = ops._k_nearest_neighbor_cuda(xyz, xyz, 16)         # self, level 1

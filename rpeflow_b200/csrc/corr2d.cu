@@ -17,6 +17,10 @@
 
 namespace b200 {
 
+// corr2d_tma.cu: the persistent TMA-fed kernel (md = 4, C % 4 == 0, 16-byte aligned inputs)
+bool corr2d_tma_eligible(const float* in1, const float* in2, int B, int C, int H, int W, int md);
+cudaError_t corr2d_fwd_tma(const float* in1, const float* in2, float* out, int B, int C, int H, int W, cudaStream_t st);
+
 constexpr int C2_TH = 8, C2_PX = 6, C2_TW = 4 * C2_PX, C2_CC = 16;   // 9 warps/CTA cap a thread at 168 registers: 6-pixel strips fit
 
 template <int MD>
@@ -268,6 +272,11 @@ extern "C" int b200_corr2d_fwd(const float* in1, const float* in2, float* out, i
     B200_REQUIRE(md >= 1 && md <= 4, "b200_corr2d_fwd: max_displacement must be in [1,4] (got %d)", md);
     if (B == 0) return B200_OK;
     cudaError_t e;
+    if (corr2d_tma_eligible(in1, in2, B, C, H, W, md)) {
+        e = corr2d_fwd_tma(in1, in2, out, B, C, H, W, as_stream(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "b200_corr2d_fwd(tma)");
+        return B200_OK;
+    }
     switch (md) {
         case 1: e = launch_corr2d_fwd<1>(in1, in2, out, B, C, H, W, as_stream(stream)); break;
         case 2: e = launch_corr2d_fwd<2>(in1, in2, out, B, C, H, W, as_stream(stream)); break;
