@@ -85,6 +85,16 @@ B200_API int b200_fps(const float* xyz, int64_t* idx, int B, int N, int n_sample
 B200_API int b200_knn(const float* input_xyz, const float* query_xyz, int64_t* idx,
              int B, int M, int Q, int D, int k, b200_stream_t stream);
 
+/* a4, production path: the same search with the same bit-exact result, but over a uniform cell grid built from the
+ * inputs (exact early termination, brute force only as the limit case; see csrc/knn_grid.cu for the bound).
+ *   scratch : >= b200_knn_scratch_bytes(B,M,Q,D,k) bytes, 256-byte aligned (cell-ordered copies of the inputs and,
+ *             for D=3, of the queries; per-cloud cell table).  Contents are undefined afterwards.
+ */
+B200_API int64_t b200_knn_scratch_bytes(int B, int M, int Q, int D, int k);
+B200_API int b200_knn_grid(const float* input_xyz, const float* query_xyz, int64_t* idx,
+                  void* scratch, int64_t scratch_bytes,
+                  int B, int M, int Q, int D, int k, b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * a6  batched index gathers.  Elements are 4 bytes wide and moved bit-exactly (fp32 or int32 data).
  * Replaces: models/utils.py:119-137 (batch_indexing_channel_first) and :101-116 (.._channel_last).

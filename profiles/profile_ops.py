@@ -46,6 +46,12 @@ def once():
     ops._correlation_forward_cuda(f1, f2, 4)
     if ONLY == "corr2d":
         return
+    if ONLY == "knn":
+        ops._k_nearest_neighbor_cuda(xyz_big, xyz, 16)
+        ops._k_nearest_neighbor_cuda(xyz, xyz, 16)
+        ops._k_nearest_neighbor_cuda(xyz, xyz, 3)
+        ops._k_nearest_neighbor_cuda(xy, grid, 1)
+        return
     ops._furthest_point_sampling_cuda(pc, 4096)
     ops._k_nearest_neighbor_cuda(xyz_big, xyz, 16)             # pyramid 8192 -> 4096
     knn11 = ops._k_nearest_neighbor_cuda(xyz, xyz, 16)         # self, level 1

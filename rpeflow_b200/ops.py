@@ -22,7 +22,7 @@ from ._lib import check, lib
 __all__ = [
     "correlation2d", "furthest_point_sampling", "k_nearest_neighbor", "squared_distance", "CorrelationFunction",
     "_correlation_forward_cuda", "_correlation_backward_cuda", "_furthest_point_sampling_cuda",
-    "_k_nearest_neighbor_cuda",
+    "_k_nearest_neighbor_cuda", "knn_bruteforce",
 ]
 
 
@@ -85,12 +85,31 @@ def _furthest_point_sampling_cuda(points_xyz, n_samples):
     return out
 
 
-def _k_nearest_neighbor_cuda(input_xyz, query_xyz, k):
-    """input [B,M,D], query [B,Q,D] -> [B,Q,k] int64 (replaces k_nearest_neighbor.cpp:6-24)."""
+def _knn_check(input_xyz, query_xyz):
     _cuda_f32(input_xyz, "input_xyz")
     _cuda_f32(query_xyz, "query_xyz")
     _require(input_xyz.dim() == 3 and query_xyz.dim() == 3 and input_xyz.shape[0] == query_xyz.shape[0]
              and input_xyz.shape[2] == query_xyz.shape[2], "input_xyz/query_xyz must be [B,M,D]/[B,Q,D]")
+
+
+def _k_nearest_neighbor_cuda(input_xyz, query_xyz, k):
+    """input [B,M,D], query [B,Q,D] -> [B,Q,k] int64 (replaces k_nearest_neighbor.cpp:6-24).  Exact search over a
+    cell grid (b200_knn_grid); bit-identical to the brute-force scan of knn_bruteforce()."""
+    _knn_check(input_xyz, query_xyz)
+    B, M, D = input_xyz.shape
+    Q = query_xyz.shape[1]
+    out = torch.empty((B, Q, int(k)), dtype=torch.int64, device=query_xyz.device)
+    nbytes = lib.b200_knn_scratch_bytes(B, M, Q, D, int(k))
+    scratch = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=query_xyz.device)     # torch blocks are 512-B aligned
+    with torch.cuda.device(query_xyz.device):
+        check(lib.b200_knn_grid(input_xyz.data_ptr(), query_xyz.data_ptr(), out.data_ptr(), scratch.data_ptr(), nbytes,
+                                B, M, Q, D, int(k), _stream(query_xyz)), "b200_knn_grid")
+    return out
+
+
+def knn_bruteforce(input_xyz, query_xyz, k):
+    """Same contract through the brute-force kernels (b200_knn): every query scans every input."""
+    _knn_check(input_xyz, query_xyz)
     B, M, D = input_xyz.shape
     Q = query_xyz.shape[1]
     out = torch.empty((B, Q, int(k)), dtype=torch.int64, device=query_xyz.device)

@@ -106,6 +106,75 @@ def test_knn_full_size_properties():
     np.testing.assert_array_equal(idx[sel].cpu().numpy(), spec.knn(pts[sel].numpy(), pts[sel].numpy(), 16))
 
 
+def _knn_adversarial_cases():
+    """Inputs chosen to break a cell-grid search: duplicates, clusters + far outliers, degenerate extents, queries
+    far outside the inputs' bounding box, huge offsets (coarse fp32 spacing), tiny extents, M < k, inf/NaN."""
+    rng = np.random.default_rng(77)
+    cases = {}
+    a = rng.random((2, 3000, 3), dtype=np.float32)
+    a[:, 1500:] = a[:, :1500]                                        # every point twice
+    cases["duplicates"] = (a, a[:, ::3].copy(), 16)
+    c = (rng.standard_normal((1, 4000, 3)) * 0.01).astype(np.float32)
+    c[0, :5] = np.float32([[50, 50, 50], [-80, 3, 1], [0, 0, 900], [1e4, -1e4, 0], [7, 7, 7]])     # outliers blow up the box
+    cases["cluster_outliers"] = (c, c[:, :600].copy(), 16)
+    pl = rng.random((1, 2048, 3), dtype=np.float32)
+    pl[..., 2] = 3.25                                                # planar cloud: one zero extent
+    cases["planar"] = (pl, rng.random((1, 300, 3), dtype=np.float32), 8)
+    ln = np.zeros((1, 1500, 3), np.float32)
+    ln[..., 0] = rng.random((1, 1500), dtype=np.float32)             # points on a line
+    cases["line"] = (ln, ln[:, :200].copy() + np.float32([0, 0.1, 0]), 3)
+    cases["all_identical"] = (np.full((1, 500, 3), 2.5, np.float32), rng.random((1, 40, 3), dtype=np.float32), 16)
+    far = rng.random((1, 2000, 3), dtype=np.float32)
+    cases["queries_outside"] = (far, (rng.random((1, 500, 3), dtype=np.float32) * 40 - 20).astype(np.float32), 16)
+    off = (rng.random((1, 3000, 3), dtype=np.float32) + np.float32(4096.0)).astype(np.float32)   # spacing 2^-11: many exact ties
+    cases["large_offset_ties"] = (off, off[:, :500].copy(), 16)
+    tiny = (rng.random((1, 1000, 3), dtype=np.float32) * np.float32(1e-12)).astype(np.float32)
+    cases["tiny_extent"] = (tiny, tiny[:, :100].copy(), 4)
+    cases["m_less_than_k"] = (rng.random((2, 7, 3), dtype=np.float32), rng.random((2, 50, 3), dtype=np.float32), 16)
+    lat = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(16), indexing="ij"), -1).reshape(1, -1, 3).astype(np.float32)
+    cases["integer_lattice_ties"] = (lat, lat[:, ::7].copy(), 32)    # equidistant neighbours everywhere
+    px = rng.random((2, 4096, 2), dtype=np.float32) * np.float32([239, 143])
+    ys, xs = np.meshgrid(np.arange(144, dtype=np.float32), np.arange(240, dtype=np.float32), indexing="ij")
+    grid = np.broadcast_to(np.stack([xs, ys], -1).reshape(1, -1, 2), (2, 144 * 240, 2)).copy()
+    cases["pixels_to_points_2d"] = (px, grid, 1)
+    half = px.copy()
+    half[..., 0] *= 0.25                                             # projected points cover a quarter of the image
+    cases["pixels_sparse_cover_2d"] = (half, grid, 1)
+    sk = rng.random((1, 5000, 3), dtype=np.float32) * np.float32([30, 17, 90]) + np.float32([-15, -8.5, 22])
+    cases["ids_shaped_cross"] = (sk, (sk[:, :2048] + rng.standard_normal((1, 2048, 3)).astype(np.float32) * 0.3).astype(np.float32), 16)
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_knn_adversarial_cases()))
+def test_knn_grid_adversarial_exact(name):
+    inp, qry, k = _knn_adversarial_cases()[name]
+    want = spec.knn(inp, qry, k)
+    got = b200.ops._k_nearest_neighbor_cuda(cu(inp), cu(qry), k).cpu().numpy()         # cell-grid search
+    np.testing.assert_array_equal(got, want)
+    brute = b200.ops.knn_bruteforce(cu(inp), cu(qry), k).cpu().numpy()                  # every query scans every input
+    np.testing.assert_array_equal(brute, want)
+
+
+def test_knn_grid_nonfinite_inputs_match_bruteforce():
+    rng = np.random.default_rng(3)
+    inp = rng.random((1, 600, 3), dtype=np.float32)
+    inp[0, 5] = np.float32([np.inf, 0, 0])
+    inp[0, 9] = np.float32([np.nan, 1, 1])
+    qry = rng.random((1, 64, 3), dtype=np.float32)
+    got = b200.ops._k_nearest_neighbor_cuda(cu(inp), cu(qry), 8).cpu().numpy()
+    brute = b200.ops.knn_bruteforce(cu(inp), cu(qry), 8).cpu().numpy()
+    np.testing.assert_array_equal(got, brute)
+    assert not np.isin(got, [5, 9]).any()                            # an inf/NaN distance never enters a list
+
+
+@pytest.mark.parametrize("B,M,Q,D,k", [(2, 1000, 513, 3, 16), (1, 4096, 1000, 2, 16), (2, 700, 1500, 2, 1), (1, 1025, 33, 3, 2)])
+def test_knn_bruteforce_random_exact(B, M, Q, D, k):
+    rng = np.random.default_rng(B * 1000 + M + Q + k)
+    inp = rng.random((B, M, D), dtype=np.float32)
+    qry = rng.random((B, Q, D), dtype=np.float32)
+    np.testing.assert_array_equal(b200.ops.knn_bruteforce(cu(inp), cu(qry), k).cpu().numpy(), spec.knn(inp, qry, k))
+
+
 def test_knn_errors():
     x = torch.rand(1, 10, 3, device=DEV)
     with pytest.raises(RuntimeError):
