@@ -16,30 +16,9 @@
 //   pass 3  corr3d_stage2       : out[b,:,i] = sum_{j in knn11(i)} weight_net1(xyz1_j - xyz1_i) * P[b,j,:]
 //
 // precision 0 = fp32 FFMA throughout (this file).  Tensor-core variants of pass 2 live in corr3d_tc.cu.
-#include "common.cuh"
+#include "corr3d_common.cuh"
 
 namespace b200 {
-
-static inline int64_t align4(int64_t v) { return (v + 3) & ~int64_t(3); }
-
-struct Corr3dScratch {
-    float *A1, *G2, *P, *W2T, *W1cT, *n1WcT, *n2WcT;
-    int64_t total;
-};
-static Corr3dScratch carve(float* base, int B, int Cout, int N1, int N2) {
-    Corr3dScratch s;
-    int64_t off = 0;
-    auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align4(n); return p; };
-    s.A1 = take((int64_t)B * N1 * Cout);
-    s.G2 = take((int64_t)B * N2 * Cout);
-    s.P = take((int64_t)B * N1 * Cout);
-    s.W2T = take((int64_t)Cout * Cout);
-    s.W1cT = take(3ll * Cout);
-    s.n1WcT = take(8ll * Cout);
-    s.n2WcT = take(8ll * Cout);
-    s.total = off;
-    return s;
-}
 
 // ---- pass 0 --------------------------------------------------------------------------------------------------
 __global__ void corr3d_prep_weights(const float* __restrict__ W1, const float* __restrict__ W2,
@@ -112,28 +91,6 @@ pointwise_linear_kernel(const float* __restrict__ X, const float* __restrict__ W
             const int o = o0 + tx * 4 + j;
             if (o < Cout) out[((size_t)b * N + n) * Cout + o] = acc[i][j] + (bias ? __ldg(bias + o) : 0.0f);
         }
-    }
-}
-
-// ---- the PointConv-style weight net: hidden 8-vector of relu(Wb.relu(Wa.d+ba)+bb) -------------------------------
-__device__ __forceinline__ void weight_net_hidden(const float* __restrict__ Wa, const float* __restrict__ ba,
-                                                  const float* __restrict__ Wb, const float* __restrict__ bb,
-                                                  float dx, float dy, float dz, float* hid) {
-    float h1[8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-        float s = __ldg(ba + o);
-        s = fmaf(__ldg(Wa + o * 3 + 0), dx, s);
-        s = fmaf(__ldg(Wa + o * 3 + 1), dy, s);
-        s = fmaf(__ldg(Wa + o * 3 + 2), dz, s);
-        h1[o] = fmaxf(s, 0.0f);
-    }
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-        float s = __ldg(bb + o);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(__ldg(Wb + o * 8 + i), h1[i], s);
-        hid[o] = fmaxf(s, 0.0f);
     }
 }
 
@@ -334,10 +291,8 @@ extern "C" int b200_corr3d_fwd(const float* xyz1, const float* feat1, const floa
     B200_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "b200_corr3d_fwd: scratch must be 16-byte aligned");
     B200_REQUIRE(w->W1 && w->b1 && w->W2 && w->b2 && w->n1_Wa && w->n1_ba && w->n1_Wb && w->n1_bb && w->n1_Wc && w->n1_bc &&
                  w->n2_Wa && w->n2_ba && w->n2_Wb && w->n2_bb && w->n2_Wc && w->n2_bc, "b200_corr3d_fwd: null weight pointer");
-    if (precision != 0) {
-        set_error("b200_corr3d_fwd: precision=%d (tensor-core path) is not built in this library version", precision);
-        return B200_ENOSUP;
-    }
+    B200_REQUIRE(precision >= 0 && precision <= 2, "b200_corr3d_fwd: precision must be 0 (fp32), 1 (TF32) or 2 (3xTF32), got %d",
+                 precision);
     if (B == 0) return B200_OK;
     cudaStream_t st = as_stream(stream);
     const Corr3dScratch s = carve(scratch, B, Cout, N1, N2);
@@ -353,7 +308,9 @@ extern "C" int b200_corr3d_fwd(const float* xyz1, const float* feat1, const floa
     B200_LAUNCH_CHECK("pointwise_linear_kernel");
 
     cudaError_t e;
-    if (k <= 4) e = launch_stage1<4>(xyz1, xyz2, knn12, s, w, B, Cout, N1, N2, k, st);
+    if (precision != 0 && corr3d_stage1_tc_eligible(Cout, k, precision))
+        e = corr3d_stage1_tc(xyz1, xyz2, knn12, s, w, B, Cout, N1, N2, k, precision, st);
+    else if (k <= 4) e = launch_stage1<4>(xyz1, xyz2, knn12, s, w, B, Cout, N1, N2, k, st);
     else if (k <= 8) e = launch_stage1<8>(xyz1, xyz2, knn12, s, w, B, Cout, N1, N2, k, st);
     else if (k <= 16) e = launch_stage1<16>(xyz1, xyz2, knn12, s, w, B, Cout, N1, N2, k, st);
     else e = launch_stage1<32>(xyz1, xyz2, knn12, s, w, B, Cout, N1, N2, k, st);

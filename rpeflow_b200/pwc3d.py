@@ -50,8 +50,12 @@ def pack_weights(module):
     return out
 
 
-def correlation3d_forward(xyz1, feat1, xyz2, feat2, weights, knn12, knn11, precision=0):
-    """Functional form: all tensors CUDA fp32; weights = dict from pack_weights(); returns [B,Cout,N1]."""
+def correlation3d_forward(xyz1, feat1, xyz2, feat2, weights, knn12, knn11, precision=2):
+    """Functional form: all tensors CUDA fp32; weights = dict from pack_weights(); returns [B,Cout,N1].
+
+    precision: arithmetic of the Cout x Cout cost_mlp layer — 0 = fp32 FFMA, 1 = TF32 tensor cores (tcgen05; what cuDNN
+    does for the reference's 1x1 convs under torch's default allow_tf32), 2 = 3xTF32 tensor cores (default; within the
+    fp32 path's 1e-4 tolerance).  Shapes the tensor-core kernel does not cover (k != 16, Cout % 32 != 0) run fp32."""
     xyz1, feat1, xyz2, feat2 = (t.contiguous().float() for t in (xyz1, feat1, xyz2, feat2))
     if not xyz1.is_cuda:
         raise RuntimeError("rpeflow_b200.correlation3d_forward: CUDA tensors required — no CPU/torch fallback")
@@ -77,7 +81,7 @@ def correlation3d_forward(xyz1, feat1, xyz2, feat2, weights, knn12, knn11, preci
 
 
 class Correlation3D(nn.Module):
-    def __init__(self, in_channels, out_channels, k=16, precision=0):
+    def __init__(self, in_channels, out_channels, k=16, precision=2):
         super().__init__()
         self.k = k
         self.precision = precision

@@ -420,6 +420,25 @@ def test_corr3d_levels_vs_oracle_and_module(C, N):
     np.testing.assert_allclose(got.cpu().numpy(), lib_ref, rtol=1e-4, atol=1e-4 * scale)
 
 
+@pytest.mark.parametrize("precision,tol", [(2, 1e-4), (1, 5e-3)])
+@pytest.mark.parametrize("C,N", [(32, 4096), (64, 2048), (96, 1024), (128, 512), (192, 256), (32, 37)])
+def test_corr3d_tensor_core_paths_vs_oracle(C, N, precision, tol):
+    """tcgen05 path of the Cout x Cout layer: precision 2 (3xTF32) meets the fp32 bar (1e-4 of the output scale),
+    precision 1 (TF32 operands, what cuDNN does for the reference under torch's default allow_tf32) 5e-3."""
+    xyz1, f1, xyz2, f2, mod = _corr3d_inputs(2, C, N, 16, C)
+    knn11 = b200.k_nearest_neighbor(xyz1.to(DEV), xyz1.to(DEV), 16)
+    knn12 = b200.k_nearest_neighbor(xyz2.to(DEV), xyz1.to(DEV), 16)
+    w = b200.pwc3d.pack_weights(mod)
+    wd = {n: v.to(DEV) for n, v in w.items()}
+    got = b200.pwc3d.correlation3d_forward(xyz1.to(DEV), f1.to(DEV), xyz2.to(DEV), f2.to(DEV), wd, knn12, knn11, precision)
+    want = spec.corr3d_fwd(xyz1.numpy(), f1.numpy(), xyz2.numpy(), f2.numpy(), knn12.cpu().numpy(), knn11.cpu().numpy(),
+                           {n: v.numpy() for n, v in w.items()})
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=tol, atol=tol * scale)
+    fp32 = b200.pwc3d.correlation3d_forward(xyz1.to(DEV), f1.to(DEV), xyz2.to(DEV), f2.to(DEV), wd, knn12, knn11, 0)
+    np.testing.assert_allclose(got.cpu().numpy(), fp32.cpu().numpy(), rtol=tol, atol=tol * scale)
+
+
 def test_corr3d_is_forward_only_and_keeps_state_dict_keys():
     _, f1, _, _, mod = _corr3d_inputs(1, 8, 32, 4, 1)
     keys = set(mod.state_dict().keys())
