@@ -46,6 +46,15 @@ def once():
     ops._correlation_forward_cuda(f1, f2, 4)
     if ONLY == "corr2d":
         return
+    if ONLY == "corr3d":
+        for (c, n) in ((32, 4096), (64, 2048), (96, 1024), (128, 512), (192, 256)):
+            x = torch.rand(B, 3, n, device=dev)
+            f = torch.randn(B, c, n, device=dev)
+            torch.manual_seed(0)
+            wl = {k_: v.to(dev) for k_, v in pwc3d.pack_weights(pwc3d.Correlation3D(c, c)).items()}
+            kk = ops.k_nearest_neighbor(x, x, 16)
+            pwc3d.correlation3d_forward(x, f, x, f, wl, kk, kk, 2)
+        return
     if ONLY == "knn":
         ops._k_nearest_neighbor_cuda(xyz_big, xyz, 16)
         ops._k_nearest_neighbor_cuda(xyz, xyz, 16)

@@ -12,8 +12,8 @@
 //   meta      thread r: neighbour index j, offset d = xyz2[j] - xyz1[i], weight-net hidden vector (8 registers).
 //   produce   per K block: h1 = lrelu(A1[i] + G2[j] + W1c.d) for 128 rows x 32 channels (8 lanes per row -> every
 //             gathered G2 row segment is one coalesced 128-byte read) and the matching W2 block, both written to
-//             shared memory K-major with the 128-byte swizzle the MMA descriptors name; 2-stage ring, stage reuse
-//             gated by tcgen05.commit -> mbarrier.
+//             shared memory K-major with the 128-byte swizzle the MMA descriptors name; one stage, reuse gated by
+//             tcgen05.commit -> mbarrier (several CTAs per SM overlap each other's gather / MMA / epilogue phases).
 //   mma       one thread issues 4 (x3 for 3xTF32) tcgen05.mma per K block: D[128 x Cout] += A[128 x 8] . B[Cout x 8]^T.
 //   epilogue  tcgen05.ld 32 columns at a time: v = lrelu(D + b2) * relu(bc + Wc.hid); the 16 rows of a point are
 //             summed by recursive halving (30 shuffles per 32 columns), lane m ends with columns 2m, 2m+1 -> one
@@ -87,13 +87,13 @@ __host__ __device__ inline TcSmem tc_layout(int Cout, int split) {
     L.w_hi = (split ? 2 : 1) * a;
     L.w_lo = split ? L.w_hi + w : L.w_hi;
     L.stage_bytes = (split ? 2 : 1) * (a + w);
-    int off = 2 * L.stage_bytes;
+    int off = L.stage_bytes;                           // one stage: co-resident CTAs (not a ring) hide the gather latency
     L.epi = off;     off += Cout * 48;                 // per output channel: b2, bc, -, -, Wc[0..7]
     L.w1c = off;     off += 3 * Cout * 4;
     L.meta_j = off;  off += TC_ROWS * 4;
     L.meta_d = off;  off += TC_ROWS * 16;
     off = (off + 15) & ~15;
-    L.bars = off;    off += 64;                        // free[2], done, tmem base slot
+    L.bars = off;    off += 64;                        // free, done, tmem base slot
     L.total = off;
     return L;
 }
@@ -122,7 +122,6 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
 
     if (tid == 0) {
         tc_mbar_init(bar_free, 1);
-        tc_mbar_init(bar_free + 8, 1);
         tc_mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -161,9 +160,9 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
     const uint32_t idesc = umma_idesc_tf32(TC_ROWS, Cout);
     const int q = lane & 7;                            // 16-byte chunk (4 channels) of the 128-byte row this lane handles
     for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb & 1;
-        if (kb >= 2) tc_mbar_wait(bar_free + 8 * st, (uint32_t)(((kb >> 1) - 1) & 1));   // MMAs that read this stage are done
-        const uint32_t stage = sbase + st * L.stage_bytes;
+        constexpr int st = 0;
+        if (kb >= 1) tc_mbar_wait(bar_free, (uint32_t)((kb - 1) & 1));   // the MMAs that read the stage are done
+        const uint32_t stage = sbase;
         const int c0 = kb * TC_KB + 4 * q;
         const float4 wx = *reinterpret_cast<const float4*>(s_w1c + c0);
         const float4 wy = *reinterpret_cast<const float4*>(s_w1c + Cout + c0);
@@ -217,7 +216,7 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
                     umma_tf32(tmem, al, wh, idesc, 1u);
                 }
             }
-            umma_commit(bar_free + 8 * st);            // arrives when the MMAs issued so far have finished reading smem
+            umma_commit(bar_free);                     // arrives when the MMAs issued so far have finished reading smem
             if (kb == nkb - 1) umma_commit(bar_done);
         }
     }
