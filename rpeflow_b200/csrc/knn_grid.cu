@@ -16,13 +16,13 @@
 //                               and rescan; a block that covers the whole grid IS the brute-force scan.
 //
 // Why the early stop is exact.  cell(x) = clamp(floor(fl(fl(x - lo) * inv_h))) is monotone in x, so a point whose
-// cell differs from the query's by more than r along some axis is farther than r*H - delta along that axis, where
-// delta bounds the rounding in the two cell computations (relative 2^-24 each on magnitudes <= extent + a few H;
-// delta = 2^-19 * (extent + 16 H) is > 30x that).  Its fp32 distance is therefore >= (r*H - delta)^2 * (1 - 5u),
-// u = 2^-24 being the rounding of each of the five fp32 operations on non-negative terms.  If the k-th best
-// distance found so far is STRICTLY below thr_r = (r*H - delta)^2 * (1 - 2^-20) (rounded down), no unseen point
-// can enter the list or tie with it, so the list equals the brute-force answer.  thr_r is computed in fp64 by the
-// build kernel.  Within the scanned block the list is ordered by the full (distance, index) key, so the order in
+// cell lies beyond a face of the scanned block is farther from the query than R = (distance from the query to that
+// face's plane lo + j*H) - delta along that axis, where delta bounds the rounding in the cell computation (relative
+// 2^-24 per operation on magnitudes <= extent + a few H; delta = 2^-19 * (extent + 16 H) is > 30x that).  Its fp32
+// distance is therefore >= R^2 * (1 - 5u), u = 2^-24 being the rounding of each of the five fp32 operations on
+// non-negative terms.  If the k-th best distance found so far is STRICTLY below thr = R^2 * (1 - 2^-20) (fp64,
+// rounded down), with R the minimum over the faces that have cells behind them, no unseen point can enter the
+// list or tie with it, so the list equals the brute-force answer.  Within the scanned block the list is ordered by the full (distance, index) key, so the order in
 // which cells (and the atomically scattered points inside a cell) are visited does not matter.
 #include <math_constants.h>
 
@@ -34,14 +34,14 @@ constexpr int KG_CELLS_MAX = 16384;     // cells per cloud (64 KB shared-memory 
 constexpr int KG_GMAX = 1024;           // cells per axis
 constexpr int KG_BUILD_THREADS = 1024;
 constexpr int KG_QUERY_THREADS = 128;
-constexpr int KG_RINGS = 8;             // thresholds stored for r = 1, 2, 4, ..., 128
 
-struct KnnGridParams {                  // 64 bytes per cloud, written by the build kernel
+struct KnnGridParams {                  // 48 bytes per cloud, written by the build kernel
     float lo[3];
     float inv_h;
     int G[3];
     int cells;
-    float thr[KG_RINGS];
+    double H;                           // cell side as the cell function sees it: 1 / (double)inv_h
+    double delta;                       // bound on the rounding of the cell function, see the header comment
 };
 
 __device__ __forceinline__ int kg_cell(float x, float lo, float inv_h, int G) {
@@ -123,13 +123,8 @@ knn_grid_build_kernel(const float* __restrict__ pts, int M, int ctarget, int mak
                 }
             }
             p.cells = p.G[0] * p.G[1] * p.G[2];
-            const double H = p.inv_h > 0.0f ? 1.0 / (double)p.inv_h : 0.0;
-            const double delta = ldexp(maxext + 16.0 * H, -19);
-            for (int ri = 0; ri < KG_RINGS; ++ri) {
-                const double R = (double)(1 << ri) * H - delta;
-                p.thr[ri] = (R > 0.0 && isfinite(R) && R * R > 1e-30)        // below that fp32 products go subnormal: no relative bound
-                                ? __double2float_rd(R * R * (1.0 - ldexp(1.0, -20))) : 0.0f;
-            }
+            p.H = p.inv_h > 0.0f ? 1.0 / (double)p.inv_h : 0.0;
+            p.delta = ldexp(maxext + 16.0 * p.H, -19);
             s_p = p;
             params[b] = p;
         }
@@ -279,6 +274,25 @@ __device__ __forceinline__ KgQuery kg_load_query(const KnnGridParams& p, const f
     return q;
 }
 
+// Largest fp32 value T such that a k-th best distance < T proves the search of the (2r+1)^D block final: every
+// unseen point lies beyond one of the block's faces, i.e. farther than R = (distance from the query to the nearest
+// face that has cells behind it) - delta along that axis; its fp32 distance is >= R^2 (1 - 5u).
+template <int D>
+__device__ __forceinline__ float kg_bound(const KnnGridParams& p, const KgQuery& q, int r) {
+    double R = CUDART_INF;
+    const float qc[3] = {q.qx, q.qy, q.qz};
+    const int cc[3] = {q.cx, q.cy, q.cz};
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        if (cc[d] - r > 0) R = fmin(R, (double)qc[d] - ((double)p.lo[d] + (double)(cc[d] - r) * p.H));
+        if (cc[d] + r < p.G[d] - 1) R = fmin(R, ((double)p.lo[d] + (double)(cc[d] + r + 1) * p.H) - (double)qc[d]);
+    }
+    R -= p.delta;
+    if (!(R > 0.0) || !(R * R > 1e-30)) return 0.0f;     // below that fp32 products go subnormal: no relative bound
+    if (!isfinite(R)) return CUDART_INF_F;               // no face has cells behind it: the block is the whole grid
+    return __double2float_rd(R * R * (1.0 - 9.5367431640625e-07));
+}
+
 template <int D>
 __device__ __forceinline__ u64 kg_key(const KgQuery& q, const float4& pt) {
     const float d = D == 3 ? sqdist3_rule(q.qx, q.qy, q.qz, pt.x, pt.y, pt.z) : sqdist2_rule(q.qx, q.qy, pt.x, pt.y);
@@ -309,7 +323,7 @@ knn_grid_query_kernel(const float4* __restrict__ sorted_pts, const int* __restri
     const int Gx = s_p.G[0], Gy = s_p.G[1], Gz = s_p.G[2];
 
     u64 L[KMAX];
-    for (int r = 1, ri = 0;; r <<= 1, ++ri) {
+    for (int r = 1;; r <<= 1) {
 #pragma unroll
         for (int s = 0; s < KMAX; ++s) L[s] = s < KMAX - k ? 0ull : KG_EMPTY;
         const int x0 = max(q.cx - r, 0), x1 = min(q.cx + r, Gx - 1);
@@ -327,7 +341,7 @@ knn_grid_query_kernel(const float4* __restrict__ sorted_pts, const int* __restri
         }
         const bool whole = x0 == 0 && y0 == 0 && z0 == 0 && x1 == Gx - 1 && y1 == Gy - 1 && z1 == Gz - 1;
         const float kth = __uint_as_float((unsigned)(L[KMAX - 1] >> 32));
-        if (whole || kth < s_p.thr[min(ri, KG_RINGS - 1)]) break;     // beyond r=128 the r=128 bound is still valid
+        if (whole || kth < kg_bound<D>(s_p, q, r)) break;
     }
     kg_store<KMAX>(L, out + ((size_t)b * Q + q.orig) * k, k);
 }
@@ -358,7 +372,7 @@ knn_grid_query_batched_kernel(const float4* __restrict__ sorted_pts, const int* 
 #pragma unroll
     for (int s = 0; s < KMAX; ++s) L[s] = KG_EMPTY;
     bool done = !q.live;
-    for (int r = 1, ri = 0;; r <<= 1, ++ri) {
+    for (int r = 1;; r <<= 1) {
         const int x0 = max(q.cx - r, 0), x1 = min(q.cx + r, Gx - 1);
         const int y0 = max(q.cy - r, 0), y1 = min(q.cy + r, Gy - 1);
         const int z0 = D == 3 ? max(q.cz - r, 0) : 0, z1 = D == 3 ? min(q.cz + r, Gz - 1) : 0;
@@ -367,13 +381,21 @@ knn_grid_query_batched_kernel(const float4* __restrict__ sorted_pts, const int* 
             for (int s = 0; s < KMAX; ++s) L[s] = s < KMAX - k ? 0ull : KG_EMPTY;
         }
         u64 thr = L[KMAX - 1];
+        // rows of cells: the query's own row first (it fills the list with near points, so most later candidates
+        // fail the threshold test), then the others in storage order
         int y = y0, z = done ? z1 + 1 : z0, c = 0, e = 0, nb = 0;
+        bool home = !done;
         while (true) {
-            while (c >= e && z <= z1) {                  // next non-empty row of cells (cells x0..x1 of a row are contiguous)
-                const int rowbase = (z * Gy + y) * Gx;
-                c = __ldg(cs + rowbase + x0);
-                e = __ldg(cs + rowbase + x1 + 1);
-                if (++y > y1) { y = y0; ++z; }
+            while (c >= e && (home || z <= z1)) {        // next non-empty row (cells x0..x1 of a row are contiguous)
+                const int ry = home ? q.cy : y, rz = home ? q.cz : z;
+                const bool skip = !home && ry == q.cy && rz == q.cz;
+                const int rowbase = (rz * Gy + ry) * Gx;
+                if (!skip) {
+                    c = __ldg(cs + rowbase + x0);
+                    e = __ldg(cs + rowbase + x1 + 1);
+                }
+                if (home) home = false;
+                else if (++y > y1) { y = y0; ++z; }
             }
             const bool active = c < e;
             if (!__any_sync(FULL, active)) break;
@@ -402,7 +424,7 @@ knn_grid_query_batched_kernel(const float4* __restrict__ sorted_pts, const int* 
         if (!done) {
             const bool whole = x0 == 0 && y0 == 0 && z0 == 0 && x1 == Gx - 1 && y1 == Gy - 1 && z1 == Gz - 1;
             const float kth = __uint_as_float((unsigned)(L[KMAX - 1] >> 32));
-            done = whole || kth < s_p.thr[min(ri, KG_RINGS - 1)];      // beyond r=128 the r=128 bound is still valid
+            done = whole || kth < kg_bound<D>(s_p, q, r);
         }
         if (__all_sync(FULL, done)) break;
     }

@@ -181,6 +181,8 @@ class CostVolumeStack:
             mod = pwc3d.Correlation3D(c, c, k=cfg.k)
             self.corr3d[lvl] = {n: v.to(self.device) for n, v in pwc3d.pack_weights(mod).items()}
         self._grids = {}
+        self.concurrent = True        # independent op groups on side streams (parallel branches under graph capture)
+        self.max_streams = 6
 
     def pixel_grid(self, batch, h, w):
         key = (batch, h, w)
@@ -209,6 +211,31 @@ class CostVolumeStack:
     #   "lvl<l>" : the 2-D activations of level l      -> correlation2d, projections, samplers of that level
     # Ops inside a stage keep the reference's call order; stages only depend on "points" (and on their own group),
     # so a feeder can stream the big 2-D activations in while the point work is already running.
+    def _parallel(self, T, sections):
+        """Run independent groups of ops.  Serially when timing per op (or when concurrency is off); otherwise each
+        group on its own side stream, forked from and joined back to the current stream — inside a CUDA-graph
+        capture these become parallel branches, which is what keeps the SMs busy through the many small launches
+        (32-CTA grid builds, coarse pyramid levels)."""
+        if not self.concurrent or T.enabled or len(sections) < 2:
+            for fn in sections:
+                fn()
+            return
+        main = torch.cuda.current_stream(self.device)
+        streams = self._streams(min(len(sections), self.max_streams))
+        for st in streams:
+            st.wait_stream(main)
+        for i, fn in enumerate(sections):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                fn()
+        for st in streams:
+            main.wait_stream(st)
+
+    def _streams(self, n):
+        pool = self.__dict__.setdefault("_stream_pool", [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device=self.device))
+        return pool[:n]
+
     def _stage_points(self, x, S, T):
         cfg = self.cfg
         B = x["pcs"].shape[0]
@@ -224,36 +251,42 @@ class CostVolumeStack:
             xyzs2.append(T("gather_xyz", projection.batch_indexing_channel_first, pc2, idx2[:, :n]))
         S["xyzs1"], S["xyzs2"] = xyzs1, xyzs2
 
-        for lvl in range(5):                                                                 # FeaturePyramid3D, pointconv.py:46
-            for xyzs in (xyzs1, xyzs2):
+        def pyramid(xyzs):                                                                   # FeaturePyramid3D, pointconv.py:46
+            for lvl in range(5):
                 T("knn_pyramid_k16", ops.k_nearest_neighbor, xyzs[lvl], xyzs[lvl + 1], cfg.k)
 
-        for lvl in range(5, 0, -1):
+        def pixels(lvl):                                                                     # RPEFlow_core.py:316-330
             h, w = cfg.level_hw(lvl)
-            xyz1, xyz2 = xyzs1[lvl], xyzs2[lvl]
-            f1_3d, f2_3d = x["feat3d"][lvl][0], x["feat3d"][lvl][1]
 
-            def to_pixels(xyz):                                                              # RPEFlow_core.py:316-324
+            def to_pixels(xyz):
                 px = (xyz[:, 0:1] + (ws - 1) / 2) * ((w - 1) / (ws - 1))
                 py = (xyz[:, 1:2] + (hs - 1) / 2) * ((h - 1) / (hs - 1))
                 return torch.cat([px, py], dim=1)
-            xy1, xy2 = to_pixels(xyz1), to_pixels(xyz2)
+            xy1, xy2 = to_pixels(xyzs1[lvl]), to_pixels(xyzs2[lvl])
             grid = self.pixel_grid(B, h, w)
             nn1 = T("knn_2d_k1", ops.k_nearest_neighbor, xy1.transpose(1, 2).contiguous(), grid, 1)      # :329
             nn2 = T("knn_2d_k1", ops.k_nearest_neighbor, xy2.transpose(1, 2).contiguous(), grid, 1)      # :330
-            knn11 = T("knn_self_k16", ops.k_nearest_neighbor, xyz1, xyz1, cfg.k)                         # :331
-            S["out"]["knn_self"][lvl] = knn11
-            if lvl < 5:                                                                       # :354-358 (k=3 searches only)
-                T("knn_interp_k3", ops.k_nearest_neighbor, xyzs1[lvl + 1], xyz1, 3)
-                T("knn_interp_k3", ops.k_nearest_neighbor, xyz1, xyz2, 3)
-            knn12 = T("knn_cross_k16", ops.k_nearest_neighbor, xyz2, xyz1, cfg.k)                        # pwc3d_core.py:81
-            cost3d = T("corr3d", pwc3d.correlation3d_forward, xyz1, f1_3d, xyz2, f2_3d, self.corr3d[lvl], knn12, knn11,
-                       cfg.precision)                                                                    # :361
-            S["out"]["corr3d"][lvl] = cost3d
             S[lvl] = {"xy1": xy1, "xy2": xy2, "nn1": nn1[..., 0], "nn2": nn2[..., 0]}
 
-        for i in range(5):                                                                    # :429-430
-            T("knn_interp_k3", ops.k_nearest_neighbor, xyzs1[i + 1], xyzs1[i], 3)
+        def cost3d(lvl):
+            xyz1, xyz2 = xyzs1[lvl], xyzs2[lvl]
+            f1_3d, f2_3d = x["feat3d"][lvl][0], x["feat3d"][lvl][1]
+            knn11 = T("knn_self_k16", ops.k_nearest_neighbor, xyz1, xyz1, cfg.k)                         # :331
+            S["out"]["knn_self"][lvl] = knn11
+            knn12 = T("knn_cross_k16", ops.k_nearest_neighbor, xyz2, xyz1, cfg.k)                        # pwc3d_core.py:81
+            S["out"]["corr3d"][lvl] = T("corr3d", pwc3d.correlation3d_forward, xyz1, f1_3d, xyz2, f2_3d, self.corr3d[lvl],
+                                        knn12, knn11, cfg.precision)                                     # :361
+
+        def interp(lvl):
+            if lvl < 5:                                                                       # :354-358 (k=3 searches only)
+                T("knn_interp_k3", ops.k_nearest_neighbor, xyzs1[lvl + 1], xyzs1[lvl], 3)
+                T("knn_interp_k3", ops.k_nearest_neighbor, xyzs1[lvl], xyzs2[lvl], 3)
+            T("knn_interp_k3", ops.k_nearest_neighbor, xyzs1[lvl], xyzs1[lvl - 1], 3)         # final upsampling, :429-430
+
+        sections = [lambda: pyramid(xyzs1), lambda: pyramid(xyzs2)]
+        for lvl in range(5, 0, -1):
+            sections += [lambda lvl=lvl: pixels(lvl), lambda lvl=lvl: cost3d(lvl), lambda lvl=lvl: interp(lvl)]
+        self._parallel(T, sections)
 
     def _stage_events(self, x, S, T):
         S["out"]["event_voxel"] = T("event_voxel", self.voxelise, x)
@@ -271,18 +304,27 @@ class CostVolumeStack:
         ef_2d = x["efeat2d"][lvl]
         dec_2d, dec_3d = x["flowfeat"][lvl]
         cost2d, cost3d = S["out"]["corr2d"][lvl], S["out"]["corr3d"][lvl]
-        p = [T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, f1_2d, f1_3d, nn1),            # :334
-             T("project_nn_corr", projection.project_feat_with_nn_corr, xy2, f2_2d, f2_3d, nn2)]            # :335
-        s = [T("grid_sample", projection.grid_sample_wrapper, f1_2d, xy1),                                  # :336
-             T("grid_sample", projection.grid_sample_wrapper, f2_2d, xy2)]                                  # :337
-        flow3d_to_2d = xyz1[:, :2]                                                            # stand-in for the 2 flow channels
-        p.append(T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, cost2d,
-                   torch.cat([cost3d, flow3d_to_2d], dim=1), nn1))                                         # :373 / :80
-        s.append(T("grid_sample", projection.grid_sample_wrapper,
-                   torch.cat([cost2d, f1_2d[:, :2]], dim=1), xy1))                                         # :376 / :107 (81+2 ch)
-        s.append(T("grid_sample", projection.grid_sample_wrapper, ef_2d, xy1))                             # :108
-        p.append(T("project_nn_corr", projection.project_feat_with_nn_corr, xy1, dec_2d, dec_3d, nn1))     # :394
-        s.append(T("grid_sample", projection.grid_sample_wrapper, dec_2d, xy1))                            # :395
+        p, s = [None] * 4, [None] * 5
+        PR, GS = projection.project_feat_with_nn_corr, projection.grid_sample_wrapper
+
+        def a():
+            p[0] = T("project_nn_corr", PR, xy1, f1_2d, f1_3d, nn1)                                        # :334
+            s[0] = T("grid_sample", GS, f1_2d, xy1)                                                        # :336
+            s[3] = T("grid_sample", GS, ef_2d, xy1)                                                        # :108
+
+        def b():
+            p[1] = T("project_nn_corr", PR, xy2, f2_2d, f2_3d, nn2)                                        # :335
+            s[1] = T("grid_sample", GS, f2_2d, xy2)                                                        # :337
+
+        def c():
+            flow3d_to_2d = xyz1[:, :2]                                                        # stand-in for the 2 flow channels
+            p[2] = T("project_nn_corr", PR, xy1, cost2d, torch.cat([cost3d, flow3d_to_2d], dim=1), nn1)    # :373 / :80
+            s[2] = T("grid_sample", GS, torch.cat([cost2d, f1_2d[:, :2]], dim=1), xy1)                     # :376 / :107 (81+2 ch)
+
+        def d():
+            p[3] = T("project_nn_corr", PR, xy1, dec_2d, dec_3d, nn1)                                      # :394
+            s[4] = T("grid_sample", GS, dec_2d, xy1)                                                       # :395
+        self._parallel(T, [a, b, c, d])
         S["out"]["proj"][lvl], S["out"]["sample"][lvl] = p, s
 
     @staticmethod
