@@ -144,42 +144,66 @@ sample_point_major_kernel(const float* __restrict__ feat, const float* __restric
     }
 }
 
-// a8, pass 2: one thread per pixel.
+// a8, pass 2: one thread per pixel.  blockIdx.z = 0: pixel offsets + channel-mean correlation; blockIdx.z >= 1: copies
+// a slab of 32 feat3d channels of the nearest point.  Batch items are visited last-to-first: pass 1 has just
+// streamed feat2d through L2 in ascending order, so the tail of the batch is still resident when this kernel starts.
+constexpr int PN_SLAB = 32;
+
 __global__ void __launch_bounds__(256)
 project_nn_corr_kernel(const float* __restrict__ xy, const float* __restrict__ feat2d, const float* __restrict__ feat3d,
                        const int64_t* __restrict__ nn, const float* __restrict__ S, float* __restrict__ out,
                        int C2, int C3, int H, int W, int N) {
-    const int b = blockIdx.y;
+    const int b = gridDim.y - 1 - blockIdx.y;
     const int HW = H * W;
     const int p = blockIdx.x * 256 + threadIdx.x;
     if (p >= HW) return;
     int64_t j = __ldg(nn + (size_t)b * HW + p);
     if (j < 0) j += N;
     j = j < 0 ? 0 : (j >= N ? N - 1 : j);
-    const float px = (float)(p % W), py = (float)(p / W);              // mesh_grid: x in channel 0 (models/utils.py:177-179)
     float* o = out + (size_t)b * (C3 + 3) * HW + p;
-    o[0] = __ldg(xy + ((size_t)b * 2 + 0) * N + j) - px;
-    o[(size_t)HW] = __ldg(xy + ((size_t)b * 2 + 1) * N + j) - py;
 
-    const float* s = S + ((size_t)b * N + j) * C2;
-    const float* f = feat2d + (size_t)b * C2 * HW + p;
-    float acc = 0.0f;
-    int c = 0;
-    if ((C2 & 3) == 0) {
-        for (; c < C2; c += 4) {                                        // 128-bit reads of the gathered row
-            const float4 sv = __ldg(reinterpret_cast<const float4*>(s + c));
-            acc += sv.x * __ldg(f + (size_t)(c + 0) * HW);
-            acc += sv.y * __ldg(f + (size_t)(c + 1) * HW);
-            acc += sv.z * __ldg(f + (size_t)(c + 2) * HW);
-            acc += sv.w * __ldg(f + (size_t)(c + 3) * HW);
+    if (blockIdx.z == 0) {
+        const float px = (float)(p % W), py = (float)(p / W);          // mesh_grid: x in channel 0 (models/utils.py:177-179)
+        o[0] = __ldg(xy + ((size_t)b * 2 + 0) * N + j) - px;
+        o[(size_t)HW] = __ldg(xy + ((size_t)b * 2 + 1) * N + j) - py;
+        const float* s = S + ((size_t)b * N + j) * C2;
+        const float* f = feat2d + (size_t)b * C2 * HW + p;
+        float acc = 0.0f;
+        int c = 0;
+        if ((C2 & 3) == 0) {
+            for (; c + 8 <= C2; c += 8) {                               // 8 plane reads in flight per thread
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + c));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + c + 4));
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(f + (size_t)(c + u) * HW);
+                acc += s0.x * v[0]; acc += s0.y * v[1]; acc += s0.z * v[2]; acc += s0.w * v[3];
+                acc += s1.x * v[4]; acc += s1.y * v[5]; acc += s1.z * v[6]; acc += s1.w * v[7];
+            }
+            for (; c < C2; c += 4) {
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(s + c));
+                acc += sv.x * __ldg(f + (size_t)(c + 0) * HW);
+                acc += sv.y * __ldg(f + (size_t)(c + 1) * HW);
+                acc += sv.z * __ldg(f + (size_t)(c + 2) * HW);
+                acc += sv.w * __ldg(f + (size_t)(c + 3) * HW);
+            }
+        } else {
+            for (; c < C2; ++c) acc += __ldg(s + c) * __ldg(f + (size_t)c * HW);
         }
-    } else {
-        for (; c < C2; ++c) acc += __ldg(s + c) * __ldg(f + (size_t)c * HW);
+        o[(size_t)2 * HW] = __fdiv_rn(acc, (float)C2);                  // torch.mean over channels
+        return;
     }
-    o[(size_t)2 * HW] = __fdiv_rn(acc, (float)C2);                      // torch.mean over channels
-
+    const int k0 = (blockIdx.z - 1) * PN_SLAB, k1 = min(k0 + PN_SLAB, C3);
     const float* g = feat3d + (size_t)b * C3 * N + j;
-    for (int k = 0; k < C3; ++k) o[(size_t)(3 + k) * HW] = __ldg(g + (size_t)k * N);
+    int k = k0;
+    for (; k + 8 <= k1; k += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(g + (size_t)(k + u) * N);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) __stcs(o + (size_t)(3 + k + u) * HW, v[u]);
+    }
+    for (; k < k1; ++k) __stcs(o + (size_t)(3 + k) * HW, __ldg(g + (size_t)k * N));
 }
 
 static int pick_csplit(int64_t cols, int B, int C) {
@@ -248,8 +272,8 @@ extern "C" int b200_project_nn_corr(const float* xy, const float* feat2d, const 
     cudaStream_t st = as_stream(stream);
     sample_point_major_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, st>>>(feat2d, xy, scratch, C2, H, W, N);
     B200_LAUNCH_CHECK("b200_project_nn_corr(sample)");
-    project_nn_corr_kernel<<<dim3(ceil_div((int64_t)H * W, 256), B), 256, 0, st>>>(xy, feat2d, feat3d, nn, scratch, out,
-                                                                                 C2, C3, H, W, N);
+    project_nn_corr_kernel<<<dim3(ceil_div((int64_t)H * W, 256), B, 1 + ceil_div(C3, PN_SLAB)), 256, 0, st>>>(
+        xy, feat2d, feat3d, nn, scratch, out, C2, C3, H, W, N);
     B200_LAUNCH_CHECK("b200_project_nn_corr");
     return B200_OK;
 }
