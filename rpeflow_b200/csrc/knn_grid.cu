@@ -473,13 +473,17 @@ static cudaError_t kg_run(const float* input, const float* query, int64_t* idx, 
     if (e != cudaSuccess) return e;
     const int ctarget = k / 2 < 2 ? 2 : (k / 2 > 16 ? 16 : k / 2);
     knn_grid_build_kernel<D><<<B, KG_BUILD_THREADS, smem, st>>>(input, M, ctarget, 1, s.params, s.cell_start, s.sorted_pts);
-    if (s.sorted_q)        // queries into the inputs' cells (their own cell_start is not needed)
-        knn_grid_build_kernel<D><<<B, KG_BUILD_THREADS, smem, st>>>(query, Q, ctarget, 0, s.params, nullptr, s.sorted_q);
-    if (k == 1) kg_launch_query<D, 1>(s, query, idx, B, M, Q, k, st);
-    else if (k <= 4) kg_launch_query<D, 4>(s, query, idx, B, M, Q, k, st);
-    else if (k <= 8) kg_launch_query<D, 8>(s, query, idx, B, M, Q, k, st);
-    else if (k <= 16) kg_launch_query<D, 16>(s, query, idx, B, M, Q, k, st);
-    else kg_launch_query<D, 32>(s, query, idx, B, M, Q, k, st);
+    KnnGridScratch q = s;
+    if (s.sorted_q) {
+        if (query == input && Q == M) q.sorted_q = s.sorted_pts;    // self search: the inputs' cell order is the queries'
+        else                                                         // queries into the inputs' cells (no cell table needed)
+            knn_grid_build_kernel<D><<<B, KG_BUILD_THREADS, smem, st>>>(query, Q, ctarget, 0, s.params, nullptr, s.sorted_q);
+    }
+    if (k == 1) kg_launch_query<D, 1>(q, query, idx, B, M, Q, k, st);
+    else if (k <= 4) kg_launch_query<D, 4>(q, query, idx, B, M, Q, k, st);
+    else if (k <= 8) kg_launch_query<D, 8>(q, query, idx, B, M, Q, k, st);
+    else if (k <= 16) kg_launch_query<D, 16>(q, query, idx, B, M, Q, k, st);
+    else kg_launch_query<D, 32>(q, query, idx, B, M, Q, k, st);
     return cudaGetLastError();
 }
 
