@@ -143,8 +143,23 @@ def _no_fallback(name, *tensors):
 
 
 def correlation2d(input1, input2, max_displacement, cpp_impl=True):
-    """input1, input2 [B,C,H,W] -> [B,(2md+1)^2,H,W] (wrapper.py:55-72). cpp_impl is accepted and ignored."""
+    """input1, input2 [B,C,H,W] -> [B,(2md+1)^2,H,W] (wrapper.py:55-72). cpp_impl is accepted and ignored.
+
+    Without autograd (inference; the reference evaluates under torch.no_grad) and for md = 4, W % 4 == 0 the cost
+    volume is computed straight from the NCHW maps (b200_corr2d_fwd_nchw): the wrapper's two permutes are gone.
+    Otherwise: permute to NHWC and go through CorrelationFunction exactly as wrapper.py:68-70 does."""
     _no_fallback("correlation2d", input1, input2)
+    needs_grad = torch.is_grad_enabled() and (input1.requires_grad or input2.requires_grad)
+    if not needs_grad and int(max_displacement) == 4 and input1.dim() == 4 and input1.shape == input2.shape \
+            and input1.shape[3] % 4 == 0:
+        a, b = input1.contiguous().float(), input2.contiguous().float()
+        B, C, H, W = a.shape
+        out = torch.empty((B, 81, H, W), dtype=torch.float32, device=a.device)
+        if a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0:
+            with torch.cuda.device(a.device):
+                check(lib.b200_corr2d_fwd_nchw(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, 4, _stream(a)),
+                      "b200_corr2d_fwd_nchw")
+            return out
     input1 = input1.permute(0, 2, 3, 1).contiguous().float()
     input2 = input2.permute(0, 2, 3, 1).contiguous().float()
     return CorrelationFunction.apply(input1, input2, max_displacement)
