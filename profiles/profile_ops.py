@@ -25,6 +25,7 @@ xy = (torch.rand(B, N, 2, generator=g) * torch.tensor([W - 1.0, H - 1.0])).to(de
 ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
 grid = torch.stack([xs, ys], -1).reshape(1, H * W, 2).expand(B, H * W, 2).contiguous().to(dev)
 feat2d = torch.randn(B, C, H, W, generator=g).to(dev)
+feat2d_b = torch.randn(B, C, H, W, generator=g).to(dev)
 feat96 = torch.randn(B, 96, H, W, generator=g).to(dev)
 feat3d = torch.randn(B, C, N, generator=g).to(dev)
 ev = torch.zeros(1_000_000, 4)
@@ -43,8 +44,12 @@ ONLY = os.environ.get("PROFILE_ONLY", "")
 
 
 def once():
-    ops._correlation_forward_cuda(f1, f2, 4)
+    if ONLY != "corr2d_nchw":
+        ops._correlation_forward_cuda(f1, f2, 4)
     if ONLY == "corr2d":
+        return
+    if ONLY == "corr2d_nchw":
+        ops.correlation2d(feat2d, feat2d_b, 4)
         return
     if ONLY == "corr3d":
         for (c, n) in ((32, 4096), (64, 2048), (96, 1024), (128, 512), (192, 256)):

@@ -4,36 +4,39 @@
 // extension runs; this kernel takes the NCHW maps as the model holds them ("the wrapper's
 // NCHW->NHWC permutes"), so correlation2d() is a single pass: 4*H*W*(2C+81) bytes per sample.
 //
-// Same skeleton as corr2d_tma.cu — persistent CTAs, one producer warp issuing 4-D TMA boxes into a 2-stage mbarrier
-// ring, nine consumer warps (warp = row shift dy) — but the channel-major layout changes the inner loop:
-//   * a stage holds 16 channels of the in1 tile (8 x 48 px, row pitch 52 floats) and the in2 halo (16 x 56 px, row
-//     pitch 68 floats); the pitches are 13 and 17 sixteen-byte units, odd, so the 8 lanes of a quarter-warp (8 rows,
-//     same strip) read 8 different bank groups: conflict-free LDS.128 with no swizzle.
-//   * lane = (row, strip), a thread owns 12 consecutive pixels x 9 column shifts.  With pixels contiguous in shared
+// Same skeleton as corr2d_tma.cu — persistent CTAs, one producer warp issuing 4-D TMA boxes into an mbarrier
+// ring (3 stages here), nine consumer warps (warp = row shift dy) — but the channel-major layout changes the inner loop:
+//   * a stage holds 16 channels of the in1 tile (8 x 32 px, row pitch 36 floats) and the in2 halo (16 x 40 px, row
+//     pitch 44 floats); the pitches are 9 and 11 sixteen-byte units, odd, so the 8 lanes of a quarter-warp (8 rows,
+//     same strip) read 8 different bank groups: conflict-free LDS.128 with no swizzle.  3-stage ring.
+//   * lane = (row, strip), a thread owns 8 consecutive pixels x 9 column shifts.  With pixels contiguous in shared
 //     memory, FFMA2 pairs two column shifts of one pixel: acc(dx, dx+1) += a[x] (broadcast) * (b[x+dx], b[x+dx+1]).
 //     Even pixels pair (0,1)(2,3)(4,5)(6,7) and keep dx=8 scalar, odd pixels keep dx=0 scalar and pair
 //     (1,2)(3,4)(5,6)(7,8): every b pair then starts at an even pixel = an aligned 64-bit half of an LDS.128, and one
-//     register per output suffices (108 accumulator registers for 108 outputs; the channel-pair scheme of the NHWC
-//     kernel needs two).  Per channel and thread: 8 LDS.128, 48 FFMA2 + 12 FFMA — FMA-pipe bound, not LDS bound.
-//   * epilogue: a thread's 12 pixels are 3 aligned float4 per displacement: plain 16-byte streaming stores.
+//     register per output suffices (the channel-pair scheme of the NHWC kernel needs two).  Per channel and thread:
+//     6 LDS.128, 32 FFMA2 + 8 FFMA.  An FFMA2 occupies its scheduler for two issue cycles (measured:
+//     profiles/microbench), so the kernel is bound by issue slots on the busiest scheduler (3 of the 9 consumer
+//     warps share one); the short strip keeps registers at ~120 so the loop body carries no spill or fix-up moves.
+//   * epilogue: a thread's 8 pixels are 2 aligned float4 per displacement: plain 16-byte streaming stores.
 #include "tma_common.cuh"
 
 namespace b200 {
 
-constexpr int N_P = 12, N_S = 4, N_TW = N_P * N_S, N_TH = 8, N_MD = 4, N_ND = 2 * N_MD + 1;
-constexpr int N_AP = 52;                         // in1 row pitch (floats): 48 + 4  -> 13 sixteen-byte units
-constexpr int N_BP = 68;                         // in2 row pitch (floats): 56 + 12 -> 17 sixteen-byte units
+constexpr int N_P = 8, N_S = 4, N_TW = N_P * N_S, N_TH = 8, N_MD = 4, N_ND = 2 * N_MD + 1;
+constexpr int N_AP = 36;                         // in1 row pitch (floats): 32 + 4 ->  9 sixteen-byte units
+constexpr int N_BP = 44;                         // in2 row pitch (floats): 40 + 4 -> 11 sixteen-byte units
 constexpr int N_HR = N_TH + 2 * N_MD;            // 16 halo rows
 constexpr int N_CC = 16;                         // channels per stage
-constexpr int N_B_CH = N_HR * N_BP * 4;          // bytes per channel of the in2 halo (4352)
-constexpr int N_A_CH = N_TH * N_AP * 4;          // bytes per channel of the in1 tile (1664)
+constexpr int N_B_CH = N_HR * N_BP * 4;          // bytes per channel of the in2 halo (2816)
+constexpr int N_A_CH = N_TH * N_AP * 4;          // bytes per channel of the in1 tile (1152)
 constexpr int N_B_BYTES = N_CC * N_B_CH, N_A_BYTES = N_CC * N_A_CH;
-constexpr int N_STAGE = N_B_BYTES + N_A_BYTES;   // 96256
-constexpr int N_NSTAGE = 2;
+constexpr int N_STAGE = N_B_BYTES + N_A_BYTES;   // 63488
+constexpr int N_NSTAGE = 3;
 constexpr int N_CONSUMERS = N_ND;
 constexpr int N_THREADS = (N_CONSUMERS + 1) * 32;
 constexpr size_t N_SMEM = (size_t)N_NSTAGE * N_STAGE + 1024 + 64;
 static_assert(N_B_BYTES % 128 == 0 && N_STAGE % 128 == 0, "TMA destinations stay 128-byte aligned");
+static_assert(N_NSTAGE == 3, "the consumer dispatches on three compile-time stage offsets");
 
 struct NAcc {                                    // the 9 column shifts of one pixel: 4 packed pairs + 1 scalar
     u64 p[4];
@@ -50,7 +53,7 @@ __device__ __forceinline__ float4 lds_128(uint32_t addr) {
 // in channel 0 of stage 0; SOFF: byte offset of the stage (compile time -> LDS immediates).
 template <int SOFF>
 __device__ __forceinline__ void corr2d_nchw_consume(NAcc (&acc)[N_P], uint32_t pa, uint32_t pb) {
-#pragma unroll 1
+#pragma unroll 2                     // the second channel's loads are issued under the first one's FMAs
     for (int c = 0; c < N_CC; ++c) {
         float a[N_P], b[N_P + 2 * N_MD];
 #pragma unroll
@@ -102,19 +105,19 @@ corr2d_fwd_nchw_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map1) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map2) : "memory");
-            int it = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int b = tile / per_img, r = tile - b * per_img;
                 const int ty = r / tiles_x, tx = r - ty * tiles_x;
                 const int y0 = ty * N_TH, x0 = tx * N_TW;
-                for (int ch = 0; ch < nchunks; ++ch, ++it) {
-                    const int s = it & 1;
-                    const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                for (int ch = 0; ch < nchunks; ++ch) {
                     while (!mbar_test(bar_empty + 8 * s, ph ^ 1u)) __nanosleep(128);   // consumers have drained this slot
                     mbar_arrive_expect_tx(bar_full + 8 * s, N_STAGE);
                     // boxes are (x, y, channel, batch); out-of-image pixels and channels >= C arrive as zeros
                     tma_load_4d(base + s * N_STAGE, &map2, x0 - N_MD, y0 - N_MD, ch * N_CC, b, bar_full + 8 * s);
                     tma_load_4d(base + s * N_STAGE + N_B_BYTES, &map1, x0, y0, ch * N_CC, b, bar_full + 8 * s);
+                    if (++s == N_NSTAGE) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -135,16 +138,17 @@ corr2d_fwd_nchw_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     }
 
     const size_t plane = (size_t)H * W;
-    int it = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int ch = 0; ch < nchunks; ++ch, ++it) {
-            const int s = it & 1;
-            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+        for (int ch = 0; ch < nchunks; ++ch) {
             mbar_wait(bar_full + 8 * s, ph);                      // TMA bytes have landed
-            if (s == 0) corr2d_nchw_consume<0>(acc, pa, pb);
-            else        corr2d_nchw_consume<N_STAGE>(acc, pa, pb);
+            if (s == 0)      corr2d_nchw_consume<0>(acc, pa, pb);
+            else if (s == 1) corr2d_nchw_consume<N_STAGE>(acc, pa, pb);
+            else             corr2d_nchw_consume<2 * N_STAGE>(acc, pa, pb);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);        // this warp is done with the slot
+            if (++s == N_NSTAGE) { s = 0; ph ^= 1u; }
         }
         const int b = tile / per_img, r = tile - b * per_img;
         const int ty = r / tiles_x, tx = r - ty * tiles_x;
