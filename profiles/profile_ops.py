@@ -48,6 +48,8 @@ def once():
         ops._correlation_forward_cuda(f1, f2, 4)
     if ONLY == "corr2d":
         return
+    if ONLY == "":
+        ops.correlation2d(feat2d, feat2d_b, 4)                 # NCHW: what the stack launches
     if ONLY == "corr2d_nchw":
         ops.correlation2d(feat2d, feat2d_b, 4)
         return

@@ -57,12 +57,21 @@ def _corr3d_forward(self, xyz1, feat1, xyz2, feat2, knn_indices_1in1=None):
     if knn_indices_1in1 is None:
         knn_indices_1in1 = ops.k_nearest_neighbor(input_xyz=xyz1, query_xyz=xyz1, k=self.k)
     return pwc3d.correlation3d_forward(xyz1, feat1, xyz2, feat2, pwc3d.pack_weights(self), knn12, knn_indices_1in1,
-                                       getattr(self, "b200_precision", 0))
+                                       getattr(self, "b200_precision", 2))
 
 
 def patch_python_ops(patch_events=True):
     mutils = importlib.import_module("models.utils")
+    wrapper = importlib.import_module("models.csrc.wrapper")
+
+    def correlation2d(input1, input2, max_displacement, cpp_impl=True):
+        """wrapper.py:55-72 with the NCHW fast path (no permutes) when autograd is not involved."""
+        if input1.is_cuda and cpp_impl and not (torch.is_grad_enabled() and (input1.requires_grad or input2.requires_grad)):
+            return ops.correlation2d(input1, input2, max_displacement)
+        return wrapper_correlation2d(input1, input2, max_displacement, cpp_impl)
+    wrapper_correlation2d = wrapper.correlation2d
     replaced = {
+        "correlation2d": correlation2d,
         "batch_indexing_channel_first": _grad_aware(projection.batch_indexing_channel_first,
                                                     mutils.batch_indexing_channel_first),
         "batch_indexing_channel_last": _grad_aware(projection.batch_indexing_channel_last,
@@ -71,8 +80,8 @@ def patch_python_ops(patch_events=True):
         "project_feat_with_nn_corr": projection.project_feat_with_nn_corr if torch.cuda.is_available()
         else mutils.project_feat_with_nn_corr,
     }
-    for modname in ("models.utils", "models.RPEFlow_core", "models.pwc3d_core", "models.pointconv",
-                    "models.losses3d", "models.RPEFlow"):
+    for modname in ("models.utils", "models.RPEFlow_core", "models.pwc2d_core", "models.pwc3d_core", "models.pointconv",
+                    "models.losses3d", "models.RPEFlow", "models.csrc", "models.csrc.wrapper"):
         try:
             mod = importlib.import_module(modname)
         except Exception:
