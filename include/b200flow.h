@@ -140,6 +140,18 @@ B200_API int b200_project_nn_corr(const float* xy, const float* feat2d_nchw, con
                          int B, int C2, int C3, int H, int W, int N, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * f2  inverse-distance interpolation over k nearest neighbours.
+ * Replaces: models/utils.py:140-156 (knn_interpolation) after its k_nearest_neighbor call — the two
+ *           batch_indexing gathers, norm, clamp(1e-8), reciprocal, normalisation and weighted sum; backwarp_3d
+ *           (:159-169) is the same op on (xyz1+flow, -flow).
+ *   input_xyz [B,3,M], input_feat [B,C,M], query_xyz [B,3,Q]  (channel-first fp32), knn_idx [B,Q,k] int64 -> out [B,C,Q]
+ * Every operation is rounded separately in the reference's order (bit-exact vs the oracle).  1 <= k <= 8 (the model uses 3).
+ */
+B200_API int b200_knn_interpolate(const float* input_xyz, const float* input_feat, const float* query_xyz,
+                         const int64_t* knn_idx, float* out, int B, int C, int M, int Q, int k,
+                         b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * a5  3-D point cost volume (pwc3d_core.Correlation3D.forward), forward only.
  * Replaces: models/pwc3d_core.py:69-117 with both KNN index sets supplied by the caller
  *           (b200_knn(xyz2 as input, xyz1 as query) for knn12; knn11 as RPEFlow_core.py:331 computes it).

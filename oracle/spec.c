@@ -177,6 +177,39 @@ ORC_API void orc_gather_cl(const uint32_t* data, const int64_t* idx, uint32_t* o
 }
 
 /* ---------------------------------------------------------------------------------------------------
+ * f2 knn_interpolation — models/utils.py:140-156 (backwarp_3d :159-169 is this with xyz1+flow, -flow):
+ * inverse-distance weights over the k nearest inputs, distance = ||x_j - q|| clamped at 1e-8, weights
+ * normalised to sum 1, out[b,c,q] = sum_k w_k * feat[b,c,idx_k].  Indices are supplied by the caller. */
+ORC_API void orc_knn_interpolate(const float* in_xyz, const float* feat, const float* q_xyz, const int64_t* idx,
+                                 float* out, int B, int C, int M, int Q, int k) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int q = 0; q < Q; ++q) {
+            float w[32], wsum = 0.0f;
+            for (int s = 0; s < k; ++s) {
+                const int64_t j = idx[((size_t)b * Q + q) * k + s];
+                float d2 = 0.0f;
+                for (int a = 0; a < 3; ++a) {
+                    const float d = in_xyz[((size_t)b * 3 + a) * M + j] - q_xyz[((size_t)b * 3 + a) * Q + q];
+                    d2 += d * d;
+                }
+                float d = sqrtf(d2);
+                if (d < 1e-8f) d = 1e-8f;
+                w[s] = 1.0f / d;
+                wsum += w[s];
+            }
+            for (int c = 0; c < C; ++c) {
+                float acc = 0.0f;
+                for (int s = 0; s < k; ++s) {
+                    const int64_t j = idx[((size_t)b * Q + q) * k + s];
+                    acc += feat[((size_t)b * C + c) * M + j] * (w[s] / wsum);
+                }
+                out[((size_t)b * C + c) * Q + q] = acc;
+            }
+        }
+}
+
+/* ---------------------------------------------------------------------------------------------------
  * a7 grid_sample_wrapper — models/utils.py:288-294: normalise (2*x/(W-1) - 1), then F.grid_sample
  * bilinear, align_corners=True, zero padding, which un-normalises ((g+1)/2)*(W-1) and blends the four
  * in-bounds taps. */

@@ -160,3 +160,13 @@ def event_voxel_trilinear(x, y, t, p, bins, H, W, polarity):
     lib().orc_event_voxel_trilinear(_p(x), _p(y), _p(t), _p(p), ctypes.c_int64(x.shape[0]), _p(vox),
                                     bins, H, W, int(polarity))
     return vox
+
+
+def knn_interpolate(input_xyz, input_feat, query_xyz, idx):
+    """input_xyz [B,3,M], input_feat [B,C,M], query_xyz [B,3,Q], idx [B,Q,k] -> [B,C,Q] (models/utils.py:140-156)."""
+    input_xyz, input_feat, query_xyz, idx = _f32(input_xyz), _f32(input_feat), _f32(query_xyz), _i64(idx)
+    B, C, M = input_feat.shape
+    Q, k = idx.shape[1], idx.shape[2]
+    out = np.empty((B, C, Q), np.float32)
+    lib().orc_knn_interpolate(_p(input_xyz), _p(input_feat), _p(query_xyz), _p(idx), _p(out), B, C, M, Q, k)
+    return out

@@ -184,3 +184,20 @@ def events_to_voxel_trilinear(x, y, t, p, num_bins, height, width, event_polarit
     pos, neg = ps > 0, ps <= 0
     return torch.cat([splat(xs[pos], ys[pos], ts[pos], 2 * ps[pos] - 1),
                       splat(xs[neg], ys[neg], ts[neg], 1)], 0).numpy()
+
+
+def knn_interpolation(input_xyz, input_features, query_xyz, k=3, knn_indices=None):
+    """models/utils.py:140-156: inverse-distance interpolation over the k nearest inputs (channel-first tensors)."""
+    if knn_indices is None:
+        knn_indices = k_nearest_neighbor(input_xyz, query_xyz, k)
+    near = batch_indexing_channel_first(input_xyz, knn_indices)                  # [B,3,Q,k]
+    dist = torch.linalg.norm(near - query_xyz[..., None], dim=1).clamp(1e-8)      # [B,Q,k]
+    w = 1.0 / dist
+    w = w / torch.sum(w, dim=-1, keepdim=True)
+    feats = batch_indexing_channel_first(input_features, knn_indices)             # [B,C,Q,k]
+    return torch.sum(feats * w[:, None, :, :], dim=-1)
+
+
+def backwarp_3d(xyz1, xyz2, flow12, k=3):
+    """models/utils.py:159-169."""
+    return xyz2 + knn_interpolation(xyz1 + flow12, -flow12, xyz2, k)

@@ -2,7 +2,8 @@
 
 Public surface (same names as the reference, danqu130/RPEFlow):
   ops         correlation2d, furthest_point_sampling, k_nearest_neighbor      (models/csrc/wrapper.py)
-  projection  batch_indexing_channel_{first,last}, grid_sample_wrapper, project_feat_with_nn_corr (models/utils.py)
+  projection  batch_indexing_channel_{first,last}, grid_sample_wrapper, project_feat_with_nn_corr,
+              knn_interpolation, backwarp_3d                                  (models/utils.py)
   pwc3d       Correlation3D, build_pc_pyramid                                 (models/pwc3d_core.py)
   events      eventsToVoxel, eventsToVoxelInter                               (event_utils.py, dsec.py)
   install     install() — plug all of the above into an unmodified reference checkout
@@ -14,7 +15,7 @@ from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is m
 from .ops import (correlation2d, furthest_point_sampling, k_nearest_neighbor, squared_distance,  # noqa: F401
                   CorrelationFunction)
 from .projection import (batch_indexing_channel_first, batch_indexing_channel_last, grid_sample_wrapper,  # noqa: F401
-                         project_feat_with_nn_corr)
+                         project_feat_with_nn_corr, knn_interpolation, backwarp_3d)
 from .pwc3d import Correlation3D, build_pc_pyramid, correlation3d_forward  # noqa: F401
 from .events import eventsToVoxel, eventsToVoxelInter  # noqa: F401
 

@@ -206,6 +206,53 @@ project_nn_corr_kernel(const float* __restrict__ xy, const float* __restrict__ f
     for (; k < k1; ++k) __stcs(o + (size_t)(3 + k) * HW, __ldg(g + (size_t)k * N));
 }
 
+// f2: knn_interpolation (models/utils.py:140-156): out[b,c,q] = sum_s wn_s * feat[b,c,idx[b,q,s]], wn = normalised inverse
+// distances (clamped at 1e-8).  Thread per query (weights computed once), channels split over blockIdx.y.  Every
+// operation is rounded separately in the reference's order, so the result equals the oracle bit for bit.
+constexpr int KI_KMAX = 8;
+
+__global__ void __launch_bounds__(256)
+knn_interpolate_kernel(const float* __restrict__ in_xyz, const float* __restrict__ feat, const float* __restrict__ q_xyz,
+                       const int64_t* __restrict__ idx, float* __restrict__ out, int C, int M, int Q, int k) {
+    const int b = blockIdx.z;
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= Q) return;
+    int j[KI_KMAX];
+    float w[KI_KMAX];
+    float wsum = 0.0f;
+    const float qx = __ldg(q_xyz + ((size_t)b * 3 + 0) * Q + q), qy = __ldg(q_xyz + ((size_t)b * 3 + 1) * Q + q),
+                qz = __ldg(q_xyz + ((size_t)b * 3 + 2) * Q + q);
+#pragma unroll
+    for (int s = 0; s < KI_KMAX; ++s) {
+        if (s < k) {
+            int64_t t = __ldg(idx + ((size_t)b * Q + q) * k + s);
+            if (t < 0) t += M;
+            t = t < 0 ? 0 : (t >= M ? M - 1 : t);
+            j[s] = (int)t;
+            const float dx = __fsub_rn(__ldg(in_xyz + ((size_t)b * 3 + 0) * M + t), qx);
+            const float dy = __fsub_rn(__ldg(in_xyz + ((size_t)b * 3 + 1) * M + t), qy);
+            const float dz = __fsub_rn(__ldg(in_xyz + ((size_t)b * 3 + 2) * M + t), qz);
+            float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+            d = d < 1e-8f ? 1e-8f : d;                   // .clamp(1e-8)
+            w[s] = __fdiv_rn(1.0f, d);
+            wsum = __fadd_rn(wsum, w[s]);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < KI_KMAX; ++s)
+        if (s < k) w[s] = __fdiv_rn(w[s], wsum);
+    const float* f = feat + (size_t)b * C * M;
+    float* o = out + (size_t)b * C * Q + q;
+    for (int c = blockIdx.y; c < C; c += gridDim.y) {
+        const float* fc = f + (size_t)c * M;
+        float acc = 0.0f;
+#pragma unroll
+        for (int s = 0; s < KI_KMAX; ++s)
+            if (s < k) acc = __fadd_rn(acc, __fmul_rn(__ldg(fc + j[s]), w[s]));
+        o[(size_t)c * Q] = acc;
+    }
+}
+
 static int pick_csplit(int64_t cols, int B, int C) {
     const int64_t ctas = (int64_t)ceil_div(cols, 256) * B;
     const int64_t want = (int64_t)sm_count() * 4;
@@ -275,5 +322,20 @@ extern "C" int b200_project_nn_corr(const float* xy, const float* feat2d, const 
     project_nn_corr_kernel<<<dim3(ceil_div((int64_t)H * W, 256), B, 1 + ceil_div(C3, PN_SLAB)), 256, 0, st>>>(
         xy, feat2d, feat3d, nn, scratch, out, C2, C3, H, W, N);
     B200_LAUNCH_CHECK("b200_project_nn_corr");
+    return B200_OK;
+}
+
+extern "C" int b200_knn_interpolate(const float* input_xyz, const float* input_feat, const float* query_xyz,
+                                    const int64_t* knn_idx, float* out, int B, int C, int M, int Q, int k,
+                                    b200_stream_t stream) {
+    using namespace b200;
+    B200_REQUIRE(input_xyz && input_feat && query_xyz && knn_idx && out, "b200_knn_interpolate: null pointer");
+    B200_REQUIRE(B >= 0 && C >= 0 && M >= 1 && Q >= 0, "b200_knn_interpolate: bad sizes");
+    B200_REQUIRE(k >= 1 && k <= KI_KMAX, "b200_knn_interpolate: k must be in [1,%d] (got %d)", KI_KMAX, k);
+    B200_REQUIRE(B <= 65535, "b200_knn_interpolate: B exceeds the grid limit");
+    if (B == 0 || C == 0 || Q == 0) return B200_OK;
+    dim3 grid(ceil_div(Q, 256), pick_csplit(Q, B, C), B);
+    knn_interpolate_kernel<<<grid, 256, 0, as_stream(stream)>>>(input_xyz, input_feat, query_xyz, knn_idx, out, C, M, Q, k);
+    B200_LAUNCH_CHECK("b200_knn_interpolate");
     return B200_OK;
 }

@@ -80,6 +80,21 @@ def patch_python_ops(patch_events=True):
         "project_feat_with_nn_corr": projection.project_feat_with_nn_corr if torch.cuda.is_available()
         else mutils.project_feat_with_nn_corr,
     }
+    ref_interp, ref_backwarp = mutils.knn_interpolation, mutils.backwarp_3d
+
+    def knn_interpolation(input_xyz, input_features, query_xyz, k=3):
+        if not input_xyz.is_cuda or k > 8 or (torch.is_grad_enabled() and (input_features.requires_grad or input_xyz.requires_grad
+                                                                           or query_xyz.requires_grad)):
+            return ref_interp(input_xyz, input_features, query_xyz, k)
+        return projection.knn_interpolation(input_xyz, input_features, query_xyz, k)
+
+    def backwarp_3d(xyz1, xyz2, flow12, k=3):
+        if not xyz1.is_cuda or k > 8 or (torch.is_grad_enabled() and (flow12.requires_grad or xyz1.requires_grad
+                                                                      or xyz2.requires_grad)):
+            return ref_backwarp(xyz1, xyz2, flow12, k)
+        return projection.backwarp_3d(xyz1, xyz2, flow12, k)
+    replaced["knn_interpolation"] = knn_interpolation
+    replaced["backwarp_3d"] = backwarp_3d
     for modname in ("models.utils", "models.RPEFlow_core", "models.pwc2d_core", "models.pwc3d_core", "models.pointconv",
                     "models.losses3d", "models.RPEFlow", "models.csrc", "models.csrc.wrapper"):
         try:

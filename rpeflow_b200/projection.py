@@ -11,7 +11,7 @@ import torch
 from ._lib import check, lib
 
 __all__ = ["batch_indexing_channel_first", "batch_indexing_channel_last", "grid_sample_wrapper",
-           "project_feat_with_nn_corr"]
+           "project_feat_with_nn_corr", "knn_interpolation", "backwarp_3d"]
 
 
 def _stream(t):
@@ -106,3 +106,28 @@ def project_feat_with_nn_corr(xy, feat_2d, feat_3d, nn_indices=None):
         check(lib.b200_project_nn_corr(pts.data_ptr(), f2.data_ptr(), f3.data_ptr(), nn.data_ptr(), out.data_ptr(),
                                        scratch.data_ptr(), B, C2, C3, H, W, N, _stream(f2)), "b200_project_nn_corr")
     return out
+
+
+def knn_interpolation(input_xyz, input_features, query_xyz, k=3, knn_indices=None):
+    """input_xyz [B,3,M], input_features [B,C,M], query_xyz [B,3,Q] -> [B,C,Q] (models/utils.py:140-156): the k-nearest
+    search (cell-grid KNN) followed by ONE kernel for gathers + inverse-distance weights + weighted sum.  Forward only."""
+    if not (input_xyz.is_cuda and input_features.is_cuda and query_xyz.is_cuda):
+        raise RuntimeError("rpeflow_b200.knn_interpolation: CUDA tensors required — no CPU/torch fallback")
+    from .ops import k_nearest_neighbor
+    xin, feat, xq = (t.contiguous().float() for t in (input_xyz, input_features, query_xyz))
+    if knn_indices is None:
+        knn_indices = k_nearest_neighbor(xin, xq, k)                          # [B,Q,k]
+    idx = _prep_idx(knn_indices, xin.device)
+    B, C, M = feat.shape
+    Q = xq.shape[2]
+    assert tuple(idx.shape) == (B, Q, k) and xin.shape == (B, 3, M)
+    out = torch.empty((B, C, Q), dtype=torch.float32, device=xin.device)
+    with torch.cuda.device(xin.device):
+        check(lib.b200_knn_interpolate(xin.data_ptr(), feat.data_ptr(), xq.data_ptr(), idx.data_ptr(), out.data_ptr(),
+                                       B, C, M, Q, int(k), _stream(xin)), "b200_knn_interpolate")
+    return out
+
+
+def backwarp_3d(xyz1, xyz2, flow12, k=3):
+    """models/utils.py:159-169: xyz2 + interpolation of -flow12 from the warped cloud xyz1 + flow12."""
+    return xyz2 + knn_interpolation(xyz1 + flow12, -flow12, xyz2, k)

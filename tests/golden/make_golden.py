@@ -150,5 +150,23 @@ def events():
          vox=obj.eventsToVoxelInter(d, 5, H, W, event_polarity=False))
 
 
+def interpolation():
+    gen = g(70)
+    xyz_in = torch.rand(2, 3, 300, generator=gen) * 4
+    feat = torch.randn(2, 7, 300, generator=gen)
+    xyz_q = torch.rand(2, 3, 450, generator=gen) * 4
+    xyz_q[0, :, :5] = xyz_in[0, :, :5]                      # coincident points: the 1e-8 clamp decides the weights
+    idx = k_nearest_neighbor(xyz_in, xyz_q, 3)
+    out = mutils.knn_interpolation(xyz_in, feat, xyz_q, k=3)
+    flow = 0.1 * torch.randn(2, 3, 300, generator=gen)
+    xyz2 = xyz_in + flow + 0.01 * torch.randn(2, 3, 300, generator=gen)
+    warp = mutils.backwarp_3d(xyz_in, xyz2, flow, k=3)
+    save("knn_interpolation", input_xyz=xyz_in, input_feat=feat, query_xyz=xyz_q, idx=idx, out=out,
+         xyz2=xyz2, flow12=flow, backwarp=warp)
+
+
 if __name__ == "__main__":
-    corr2d(); fps(); knn(); gathers(); projection(); corr3d(); events()
+    only = sys.argv[1:]
+    for fn in (corr2d, fps, knn, gathers, projection, corr3d, events, interpolation):
+        if not only or fn.__name__ in only:
+            fn()

@@ -506,3 +506,26 @@ def test_event_trilinear_cfg4_size():
     assert np.all(np.abs(got - want) <= 1e-5 * np.maximum(1.0, np.abs(want)))
     # interior events splat total weight 1 each: the grid sums to (almost) n
     assert abs(float(got.sum(dtype=np.float64)) - n) < 0.02 * n
+
+
+# ------------------------------------------------------------------------------------------------- knn_interpolation (§8f rank 2)
+def test_knn_interpolation_golden_and_levels(golden):
+    g = golden("knn_interpolation")
+    got = b200.knn_interpolation(cu(g["input_xyz"]), cu(g["input_feat"]), cu(g["query_xyz"]), 3)
+    np.testing.assert_allclose(got.cpu().numpy(), g["out"], rtol=1e-6, atol=1e-6)          # the reference's own output
+    warp = b200.backwarp_3d(cu(g["input_xyz"]), cu(g["xyz2"]), cu(g["flow12"]), 3)
+    np.testing.assert_allclose(warp.cpu().numpy(), g["backwarp"], rtol=1e-6, atol=1e-6)
+    gen = torch.Generator().manual_seed(4)
+    for (B, C, M, Q, k) in [(2, 64, 2048, 4096, 3), (1, 3, 256, 512, 3), (2, 5, 40, 33, 8), (1, 192, 256, 512, 1)]:
+        xin = torch.rand(B, 3, M, generator=gen) * 10
+        feat = torch.randn(B, C, M, generator=gen)
+        xq = torch.rand(B, 3, Q, generator=gen) * 10
+        xq[:, :, :3] = xin[:, :, :3]                                                          # coincident points: clamp(1e-8)
+        idx = b200.k_nearest_neighbor(xin.to(DEV), xq.to(DEV), k)
+        got = b200.knn_interpolation(xin.to(DEV), feat.to(DEV), xq.to(DEV), k, knn_indices=idx)
+        want = spec.knn_interpolate(xin.numpy(), feat.numpy(), xq.numpy(), idx.cpu().numpy())
+        np.testing.assert_array_equal(got.cpu().numpy(), want)                                # every op rounded as the oracle does
+        ref = torch_ref.knn_interpolation(xin, feat, xq, k, knn_indices=idx.cpu())
+        np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        b200.knn_interpolation(xin, feat, xq, 3)                                              # CPU tensors: no fallback

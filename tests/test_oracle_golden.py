@@ -131,3 +131,14 @@ def test_event_voxel_trilinear(golden, name, pol):
     args = (g["x"], g["y"], g["t"], g["p"], int(g["bins"]), int(g["H"]), int(g["W"]), pol)
     np.testing.assert_allclose(spec.event_voxel_trilinear(*args), g["vox"], rtol=0, atol=1e-5)
     np.testing.assert_array_equal(torch_ref.events_to_voxel_trilinear(*args), g["vox"])
+
+
+def test_knn_interpolation_oracle_matches_reference_fixture(golden):
+    """models/utils.py:140-169.  Both restatements reproduce the reference's outputs."""
+    g = golden("knn_interpolation")
+    got = spec.knn_interpolate(g["input_xyz"], g["input_feat"], g["query_xyz"], g["idx"])
+    np.testing.assert_allclose(got, g["out"], rtol=1e-6, atol=1e-6)
+    t = lambda a: torch.from_numpy(a)
+    ref = torch_ref.knn_interpolation(t(g["input_xyz"]), t(g["input_feat"]), t(g["query_xyz"]), 3)
+    assert torch.equal(ref, t(g["out"]))
+    assert torch.equal(torch_ref.backwarp_3d(t(g["input_xyz"]), t(g["xyz2"]), t(g["flow12"]), 3), t(g["backwarp"]))
