@@ -30,7 +30,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="frame pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=74,
+                    help="frame pairs per GPU per step (74 pairs = 148 clouds: one FPS cloud per SM of a B200)")
     ap.add_argument("--workload", default="things", choices=["things", "dsec", "hd", "tiny"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-s", type=float, default=20.0, help="target seconds of CPU work for cpu_baseline")
@@ -339,7 +340,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(f"corr2d_fwd_L1_{cfg.name}_B{B}")
+            per_pair = json.load(f).get(f"corr2d_fwd_L1_{cfg.name}_per_frame_pair")
+            traffic = per_pair * B if per_pair else None
     roofline = {"kernel": "corr2d_fwd_nchw_kernel (level 1: C=32, %dx%d, batch %d)" % (*cfg.level_hw(1), B),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": corr_bytes,
