@@ -63,3 +63,34 @@ def test_graph_replay_and_feeder_match_eager_run():
         main.synchronize()
         assert _same({k: v for k, v in out.items() if k != "event_voxel"}, want)
         assert torch.equal(runners[slot].checksum[0], ints_w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["dsec", "hd"])
+def test_other_baseline_configs_run_and_index_ops_stay_exact(name):
+    """BASELINE.json configs[3] (DSEC-shaped: 640x480, tri-linear voxels) and configs[4] (1920x1080, 32768 points: FPS
+    over a 4-CTA cluster, KNN over 32768 inputs): one frame pair through the whole stack; FPS and a sample of the KNN
+    results are compared with the CPU oracle, float outputs must be finite and the voxel grid must hold every event."""
+    import numpy as np
+    from oracle import spec
+    dev = torch.device("cuda", 0)
+    cfg = CONFIGS[name]
+    host = make_host_inputs(cfg, 1)
+    stack = CostVolumeStack(cfg, dev)
+    out, _ = stack.run(to_device(host, dev))
+    torch.cuda.synchronize()
+    pcs = host["pcs"]
+    both = torch.cat([pcs[:, :3], pcs[:, 3:]], 0).transpose(1, 2).contiguous().numpy()
+    np.testing.assert_array_equal(out["fps_idx"].cpu().numpy(), spec.fps(both, 4096))
+    idx1 = out["fps_idx"][0].cpu()
+    for lvl in (1, 4):
+        n = [4096, 2048, 1024, 512, 256][lvl - 1]
+        xyz = pcs[0, :3][:, idx1[:n]].t().contiguous().numpy()[None]
+        want = spec.knn(xyz, xyz[:, :64], 16)
+        np.testing.assert_array_equal(out["knn_self"][lvl][:, :64].cpu().numpy(), want)
+    for lvl in range(1, 6):
+        for t in [out["corr2d"][lvl], out["corr3d"][lvl]] + out["proj"][lvl] + out["sample"][lvl]:
+            assert bool(torch.isfinite(t).all())
+    n_ev = cfg.n_events
+    total = float(out["event_voxel"].double().sum())
+    assert abs(total - n_ev) <= 1e-4 * n_ev if name == "hd" else total > 0     # integer-pixel voxels conserve the event count
