@@ -17,7 +17,7 @@ danqu130/RPEFlow):
   final upsampling                      5x KNN k=3 (N_{l+1} -> N_l)                          :429-430
 
 = 1 voxelisation, 1 FPS, 43 KNN, 5 corr2d, 5 Correlation3D, 20 project_feat_with_nn_corr (whose internal
-grid_sample is fused) + 25 stand-alone grid_sample_wrapper.  Everything between those calls (convolutions,
+grid_sample is fused) + 25 stand-alone grid_sample_wrapper (the 83-channel one is issued as 81 + 2 channels).  Everything between those calls (convolutions,
 attention, flow heads) is out of scope, so the feature maps the ops consume are synthetic activations.
 """
 import math
@@ -319,7 +319,10 @@ class CostVolumeStack:
         def c():
             flow3d_to_2d = xyz1[:, :2]                                                        # stand-in for the 2 flow channels
             p[2] = T("project_nn_corr", PR, xy1, cost2d, torch.cat([cost3d, flow3d_to_2d], dim=1), nn1)    # :373 / :80
-            s[2] = T("grid_sample", GS, torch.cat([cost2d, f1_2d[:, :2]], dim=1), xy1)                     # :376 / :107 (81+2 ch)
+            # :376 / :107 samples cat[cost volume, 2 flow channels] (83 ch); sampling is per channel, so the two parts are
+            # sampled separately and only the small [B,83,N] result is concatenated (the 83-channel map is never built)
+            s[2] = torch.cat([T("grid_sample", GS, cost2d, xy1),
+                              T("grid_sample", GS, f1_2d[:, :2].contiguous(), xy1)], dim=1)
 
         def d():
             p[3] = T("project_nn_corr", PR, xy1, dec_2d, dec_3d, nn1)                                      # :394
