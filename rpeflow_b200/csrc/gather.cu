@@ -99,32 +99,71 @@ __device__ __forceinline__ float blend(const float* __restrict__ plane, const Ta
     return v;
 }
 
-// a7: out[b,c,n] = bilinear(feat[b,c], xy[b,:,n])       grid: (ceil(N/256), csplit, B)
+// Two lanes per point: lane `side` owns the left (side 0) or right (side 1) tap of both rows, so the two horizontally
+// adjacent taps of a row are requested by neighbouring lanes of ONE load instruction and share a 32-byte sector
+// request (7 times out of 8) — with a thread per point every 4-byte tap pulls its own sector and these gathers are
+// bound by L2 sector bandwidth (8x over-fetch), not by HBM.
+struct HalfTaps {
+    int o0, o1;          // this side's offsets in row y0 / y1 (-1: outside the image)
+    float w0, w1;
+};
+__device__ __forceinline__ HalfTaps half_taps(const Taps& t, int side) {
+    HalfTaps h;
+    h.o0 = side ? t.o01 : t.o00; h.w0 = side ? t.w01 : t.w00;
+    h.o1 = side ? t.o11 : t.o10; h.w1 = side ? t.w11 : t.w10;
+    return h;
+}
+__device__ __forceinline__ float half_blend(const float* __restrict__ plane, const HalfTaps& h) {
+    float v = 0.0f;
+    if (h.o0 >= 0) v += __ldg(plane + h.o0) * h.w0;
+    if (h.o1 >= 0) v += __ldg(plane + h.o1) * h.w1;
+    return v;
+}
+
+// a7: out[b,c,n] = bilinear(feat[b,c], xy[b,:,n])       grid: (ceil(N/128), csplit, B); a warp covers 16 points
 __global__ void __launch_bounds__(256)
 grid_sample_pts_kernel(const float* __restrict__ feat, const float* __restrict__ xy, float* __restrict__ out,
                        int C, int H, int W, int N) {
     const int b = blockIdx.z;
-    const int n = blockIdx.x * 256 + threadIdx.x;
-    if (n >= N) return;
-    const Taps t = make_taps(__ldg(xy + ((size_t)b * 2 + 0) * N + n), __ldg(xy + ((size_t)b * 2 + 1) * N + n), H, W);
+    const int side = threadIdx.x & 1;
+    const int n = blockIdx.x * 128 + (threadIdx.x >> 1);
+    const bool ok = n < N;
+    Taps t = {-1, -1, -1, -1, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (ok) t = make_taps(__ldg(xy + ((size_t)b * 2 + 0) * N + n), __ldg(xy + ((size_t)b * 2 + 1) * N + n), H, W);
+    const HalfTaps h = half_taps(t, side);
     const size_t plane = (size_t)H * W;
     const float* f = feat + (size_t)b * C * plane;
     float* o = out + (size_t)b * C * N + n;
-    for (int c = blockIdx.y; c < C; c += gridDim.y) o[(size_t)c * N] = blend(f + (size_t)c * plane, t);
+    // two channels per step: both lanes of a point accumulate both channels, lane `side` stores channel c + side
+    int c = blockIdx.y * 2;
+    for (; c + 1 < C; c += gridDim.y * 2) {
+        float v0 = half_blend(f + (size_t)c * plane, h), v1 = half_blend(f + (size_t)(c + 1) * plane, h);
+        v0 += __shfl_xor_sync(FULL, v0, 1);
+        v1 += __shfl_xor_sync(FULL, v1, 1);
+        if (ok) o[(size_t)(c + side) * N] = side ? v1 : v0;
+    }
+    if (c < C) {                                         // odd channel count: the last channel of this CTA's slice
+        float v0 = half_blend(f + (size_t)c * plane, h);
+        v0 += __shfl_xor_sync(FULL, v0, 1);
+        if (ok && side == 0) o[(size_t)c * N] = v0;
+    }
 }
 
-// a8, pass 1: S[b,n,c] = bilinear(feat2d[b,c], xy[b,:,n])  (point-major scratch)   block (32 points, 8 channel lanes)
+// a8, pass 1: S[b,n,c] = bilinear(feat2d[b,c], xy[b,:,n])  (point-major scratch).  Block = 16 points; compute: a warp
+// owns 4 of every 32 channels, lanes = 16 points x 2 tap sides (see half_taps); write: lane = channel (contiguous in S).
 __global__ void __launch_bounds__(256)
 sample_point_major_kernel(const float* __restrict__ feat, const float* __restrict__ xy, float* __restrict__ S,
                           int C, int H, int W, int N) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[32][17];
     const int b = blockIdx.y;
-    const int n0 = blockIdx.x * 32;
-    const int tp = threadIdx.x & 31, tc = threadIdx.x >> 5;          // compute: lane = point, warp = channel lane
+    const int n0 = blockIdx.x * 16;
+    const int lane = threadIdx.x & 31, tc = threadIdx.x >> 5;
+    const int side = lane & 1, tp = lane >> 1;
     const int n = n0 + tp;
     const bool ok = n < N;
     Taps t = {-1, -1, -1, -1, 0.0f, 0.0f, 0.0f, 0.0f};
     if (ok) t = make_taps(__ldg(xy + ((size_t)b * 2 + 0) * N + n), __ldg(xy + ((size_t)b * 2 + 1) * N + n), H, W);
+    const HalfTaps h = half_taps(t, side);
     const size_t plane = (size_t)H * W;
     const float* f = feat + (size_t)b * C * plane;
     for (int c0 = 0; c0 < C; c0 += 32) {
@@ -132,14 +171,15 @@ sample_point_major_kernel(const float* __restrict__ feat, const float* __restric
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int c = c0 + tc * 4 + u;
-            tile[tc * 4 + u][tp] = (ok && c < C) ? blend(f + (size_t)c * plane, t) : 0.0f;
+            float v = c < C ? half_blend(f + (size_t)c * plane, h) : 0.0f;
+            v += __shfl_xor_sync(FULL, v, 1);
+            if (side == 0) tile[tc * 4 + u][tp] = v;
         }
         __syncthreads();
-        // write: lane = channel (contiguous in S), warp = 4 points
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int p = tc * 4 + u, c = c0 + tp;
-            if (n0 + p < N && c < C) S[((size_t)b * N + n0 + p) * C + c] = tile[tp][p];
+        for (int u = 0; u < 2; ++u) {
+            const int p = tc * 2 + u, c = c0 + lane;
+            if (n0 + p < N && c < C) S[((size_t)b * N + n0 + p) * C + c] = tile[lane][p];
         }
     }
 }
@@ -301,7 +341,8 @@ extern "C" int b200_grid_sample_pts(const float* feat, const float* xy, float* o
     B200_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1 && N >= 0, "b200_grid_sample_pts: bad sizes");
     B200_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, "b200_grid_sample_pts: plane or batch too large");
     if (B == 0 || C == 0 || N == 0) return B200_OK;
-    dim3 grid(ceil_div(N, 256), pick_csplit(N, B, C), B);
+    int csplit = pick_csplit((int64_t)N * 2, B, (C + 1) / 2);
+    dim3 grid(ceil_div(N, 128), csplit, B);
     grid_sample_pts_kernel<<<grid, 256, 0, as_stream(stream)>>>(feat, xy, out, C, H, W, N);
     B200_LAUNCH_CHECK("b200_grid_sample_pts");
     return B200_OK;
@@ -317,7 +358,7 @@ extern "C" int b200_project_nn_corr(const float* xy, const float* feat2d, const 
     B200_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "b200_project_nn_corr: scratch must be 16-byte aligned");
     if (B == 0) return B200_OK;
     cudaStream_t st = as_stream(stream);
-    sample_point_major_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, st>>>(feat2d, xy, scratch, C2, H, W, N);
+    sample_point_major_kernel<<<dim3(ceil_div(N, 16), B), 256, 0, st>>>(feat2d, xy, scratch, C2, H, W, N);
     B200_LAUNCH_CHECK("b200_project_nn_corr(sample)");
     project_nn_corr_kernel<<<dim3(ceil_div((int64_t)H * W, 256), B, 1 + ceil_div(C3, PN_SLAB)), 256, 0, st>>>(
         xy, feat2d, feat3d, nn, scratch, out, C2, C3, H, W, N);
