@@ -5,7 +5,7 @@
 // NCHW->NHWC permutes"), so correlation2d() is a single pass: 4*H*W*(2C+81) bytes per sample.
 //
 // Same skeleton as corr2d_tma.cu — persistent CTAs, one producer warp issuing 4-D TMA boxes into an mbarrier
-// ring (3 stages here), nine consumer warps (warp = row shift dy) — but the channel-major layout changes the inner loop:
+// ring (3 stages here), consumer warps per row shift dy (roles below) — but the channel-major layout changes the inner loop:
 //   * a stage holds 16 channels of the in1 tile (8 x 32 px, row pitch 36 floats) and the in2 halo (16 x 40 px, row
 //     pitch 44 floats); the pitches are 9 and 11 sixteen-byte units, odd, so the 8 lanes of a quarter-warp (8 rows,
 //     same strip) read 8 different bank groups: conflict-free LDS.128 with no swizzle.  3-stage ring.
@@ -32,9 +32,16 @@ constexpr int N_A_CH = N_TH * N_AP * 4;          // bytes per channel of the in1
 constexpr int N_B_BYTES = N_CC * N_B_CH, N_A_BYTES = N_CC * N_A_CH;
 constexpr int N_STAGE = N_B_BYTES + N_A_BYTES;   // 63488
 constexpr int N_NSTAGE = 3;
-constexpr int N_CONSUMERS = N_ND;
+// Warp roles.  Nine row shifts over four schedulers would leave one scheduler with three full warps (and the kernel is
+// bound by issue slots on the busiest scheduler), so the ninth row shift is split by CHANNELS over two warps:
+//   warps 0..7 : row shift dy = warp - 4, all 16 channels of a stage          (2 per scheduler)
+//   warp  8    : row shift +4, channels 0..7 ; adds warp 9's partial sums and stores the plane   (scheduler 0: 2.5)
+//   warp  9    : row shift +4, channels 8..15; hands its accumulators over through shared memory (scheduler 1: 2.5)
+//   warp 10    : TMA producer                                                                     (scheduler 2)
+constexpr int N_CONSUMERS = N_ND + 1;
 constexpr int N_THREADS = (N_CONSUMERS + 1) * 32;
-constexpr size_t N_SMEM = (size_t)N_NSTAGE * N_STAGE + 1024 + 64;
+constexpr int N_COMB_BYTES = 2 * N_P * N_ND * 32 * 4;   // two hand-over buffers [72 accumulators][32 lanes]
+constexpr size_t N_SMEM = (size_t)N_NSTAGE * N_STAGE + N_COMB_BYTES + 1024 + 64;
 static_assert(N_B_BYTES % 128 == 0 && N_STAGE % 128 == 0, "TMA destinations stay 128-byte aligned");
 static_assert(N_NSTAGE == 3, "the consumer dispatches on three compile-time stage offsets");
 
@@ -52,9 +59,11 @@ __device__ __forceinline__ float4 lds_128(uint32_t addr) {
 // One stage (16 channels) for one consumer thread.  pa / pb: shared addresses of the thread's first in1 / in2 pixel
 // in channel 0 of stage 0; SOFF: byte offset of the stage (compile time -> LDS immediates).
 template <int SOFF>
-__device__ __forceinline__ void corr2d_nchw_consume(NAcc (&acc)[N_P], uint32_t pa, uint32_t pb) {
+__device__ __forceinline__ void corr2d_nchw_consume(NAcc (&acc)[N_P], uint32_t pa, uint32_t pb, int c_begin, int c_end) {
+    pa += c_begin * N_A_CH;
+    pb += c_begin * N_B_CH;
 #pragma unroll 2                     // the second channel's loads are issued under the first one's FMAs
-    for (int c = 0; c < N_CC; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
         float a[N_P], b[N_P + 2 * N_MD];
 #pragma unroll
         for (int m = 0; m < N_P / 4; ++m) {
@@ -79,13 +88,14 @@ __device__ __forceinline__ void corr2d_nchw_consume(NAcc (&acc)[N_P], uint32_t p
     }
 }
 
-__global__ void __launch_bounds__(N_THREADS, 1)   // 10 warps are allocated as 12: 168 registers per thread
+__global__ void __launch_bounds__(N_THREADS, 1)   // 11 warps are allocated as 12: 168 registers per thread
 corr2d_fwd_nchw_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                        float* __restrict__ out, int C, int H, int W, int tiles_x, int tiles_y, int num_tiles, float inv_c) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_full = base + N_NSTAGE * N_STAGE;
+    const uint32_t bar_full = base + N_NSTAGE * N_STAGE + N_COMB_BYTES;
     const uint32_t bar_empty = bar_full + 8 * N_NSTAGE;
+    float* comb = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + N_NSTAGE * N_STAGE);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -124,10 +134,12 @@ corr2d_fwd_nchw_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         return;
     }
 
-    // ---------------- consumers: warp = row shift dy, lane = (row, strip)
+    // ---------------- consumers: warp -> (row shift, channel range), lane = (row, strip)
     const int row = lane & 7, strip = lane >> 3;
+    const int dyw = warp < N_ND ? warp : N_ND - 1;                // row-shift index of this warp (warps 8 and 9 share +4)
+    const int c_begin = warp == N_ND ? N_CC / 2 : 0, c_end = warp == N_ND - 1 ? N_CC / 2 : N_CC;
     const uint32_t pa = base + (uint32_t)((row * N_AP + strip * N_P) * 4);
-    const uint32_t pb = base + (uint32_t)(((row + warp) * N_BP + strip * N_P) * 4);
+    const uint32_t pb = base + (uint32_t)(((row + dyw) * N_BP + strip * N_P) * 4);
 
     NAcc acc[N_P];
 #pragma unroll
@@ -138,22 +150,56 @@ corr2d_fwd_nchw_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     }
 
     const size_t plane = (size_t)H * W;
-    int s = 0;
+    int s = 0, tcount = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
         for (int ch = 0; ch < nchunks; ++ch) {
             mbar_wait(bar_full + 8 * s, ph);                      // TMA bytes have landed
-            if (s == 0)      corr2d_nchw_consume<0>(acc, pa, pb);
-            else if (s == 1) corr2d_nchw_consume<N_STAGE>(acc, pa, pb);
-            else             corr2d_nchw_consume<2 * N_STAGE>(acc, pa, pb);
+            if (s == 0)      corr2d_nchw_consume<0>(acc, pa, pb, c_begin, c_end);
+            else if (s == 1) corr2d_nchw_consume<N_STAGE>(acc, pa, pb, c_begin, c_end);
+            else             corr2d_nchw_consume<2 * N_STAGE>(acc, pa, pb, c_begin, c_end);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);        // this warp is done with the slot
             if (++s == N_NSTAGE) { s = 0; ph ^= 1u; }
         }
+        if (warp >= N_ND - 1) {
+            // hand-over of the split row shift: warp 9 parks its 72 partial sums per lane in buffer (tile parity); the
+            // pair meets at named barrier 1.  Warp 9 rewrites a buffer two tiles later, after a meeting that warp 8 only
+            // reaches once it has consumed that buffer, so one barrier per tile is enough.
+            float* cb = comb + (size_t)(tcount & 1) * (N_P * N_ND * 32) + lane;
+            if (warp == N_ND) {
+#pragma unroll
+                for (int i = 0; i < N_P; ++i) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float l, h;
+                        unpack2(acc[i].p[q], l, h);
+                        cb[(i * N_ND + 2 * q) * 32] = l;
+                        cb[(i * N_ND + 2 * q + 1) * 32] = h;
+                        acc[i].p[q] = 0ull;
+                    }
+                    cb[(i * N_ND + 8) * 32] = acc[i].s;
+                    acc[i].s = 0.0f;
+                }
+                asm volatile("bar.sync 1, 64;" ::: "memory");
+                continue;                                         // warp 8 stores the plane
+            }
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < N_P; ++i) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float l, h;
+                    unpack2(acc[i].p[q], l, h);
+                    acc[i].p[q] = pack2(l + cb[(i * N_ND + 2 * q) * 32], h + cb[(i * N_ND + 2 * q + 1) * 32]);
+                }
+                acc[i].s += cb[(i * N_ND + 8) * 32];
+            }
+        }
         const int b = tile / per_img, r = tile - b * per_img;
         const int ty = r / tiles_x, tx = r - ty * tiles_x;
         const int y = ty * N_TH + row, x = tx * N_TW + strip * N_P;
-        float* o = out + ((size_t)b * (N_ND * N_ND) + (size_t)warp * N_ND) * plane + (size_t)y * W + x;
+        float* o = out + ((size_t)b * (N_ND * N_ND) + (size_t)dyw * N_ND) * plane + (size_t)y * W + x;
         const bool yok = y < H;
         // out(i, d): even pixel -> pair d/2 (lo: even d, hi: odd d), d = 8 scalar; odd pixel -> d = 0 scalar, pair (d-1)/2
         float lo[N_P][4], hi[N_P][4];
