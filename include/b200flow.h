@@ -140,6 +140,24 @@ B200_API int b200_project_nn_corr(const float* xy, const float* feat2d_nchw, con
                          int B, int C2, int C3, int H, int W, int N, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * f1  PointConv forward, both PointConvDownSampling and PointConvNoSampling (= sampled_xyz is xyz).
+ * Replaces: models/pointconv.py:33-61 and :90-122 after their k_nearest_neighbor call (gathers, weight net,
+ *           torch.matmul(weights, knn_features), nn.Linear(16*(C+3), out), LeakyReLU(0.1); norm = None).
+ *   xyz [B,3,N], feat [B,C,N], sampled_xyz [B,3,S] (channel-first fp32), knn [B,S,16] int64 into xyz -> out [B,Cout,S]
+ *   weights (row-major [out,in]): weight_net Wa [8,3], ba [8], Wb [16,8], bb [16]; linear L [Cout, 16*(C+3)], bias [Cout]
+ *   scratch : >= b200_pointconv_scratch_floats(B,C,Cout,N) floats, 16-byte aligned.
+ *   precision: 1 = TF32 tensor cores (tcgen05), 2 (and 0) = 3xTF32 (fp32-level accuracy).
+ * Limits: k == 16, Cout <= 256 (B200_ENOSUP otherwise).
+ */
+typedef struct b200_pointconv_weights {
+    const float *Wa, *ba, *Wb, *bb, *L, *bias;
+} b200_pointconv_weights;
+B200_API int64_t b200_pointconv_scratch_floats(int B, int C, int Cout, int N);
+B200_API int b200_pointconv_fwd(const float* xyz, const float* feat, const float* sampled_xyz, const int64_t* knn,
+                       const b200_pointconv_weights* w, float* out, float* scratch,
+                       int B, int C, int Cout, int N, int S, int k, int precision, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * f2  inverse-distance interpolation over k nearest neighbours.
  * Replaces: models/utils.py:140-156 (knn_interpolation) after its k_nearest_neighbor call — the two
  *           batch_indexing gathers, norm, clamp(1e-8), reciprocal, normalisation and weighted sum; backwarp_3d

@@ -177,6 +177,51 @@ ORC_API void orc_gather_cl(const uint32_t* data, const int64_t* idx, uint32_t* o
 }
 
 /* ---------------------------------------------------------------------------------------------------
+ * f1 PointConv — models/pointconv.py:33-61 (PointConvDownSampling.forward) and :90-122 (PointConvNoSampling.forward,
+ * which is the same computation with sampled_xyz = xyz): per sampled point p with neighbours j_k = knn[p][k]
+ *   d_k  = xyz[:,j_k] - sampled[:,p]
+ *   w_k  = lrelu(Wb . lrelu(Wa . d_k + ba) + bb)            weight_net = MLP2d(3,[8,16]), LeakyReLU(0.1) after both
+ *   M    = sum_k w_k (16) x [xyz_jk ; feat_jk] (C+3)        flattened index = w*(C+3) + c   (pointconv.py:55-57)
+ *   out  = lrelu(L . M + bias)                              nn.Linear(16*(C+3), out), norm = None, LeakyReLU(0.1) */
+ORC_API void orc_pointconv_fwd(const float* xyz, const float* feat, const float* sampled, const int64_t* knn,
+                               const float* Wa, const float* ba, const float* Wb, const float* bb,
+                               const float* L, const float* bias, float* out,
+                               int B, int C, int N, int S, int k, int Cout) {
+    const int Cf = C + 3;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int p = 0; p < S; ++p) {
+            float* M = (float*)calloc((size_t)16 * Cf, sizeof(float));
+            for (int s = 0; s < k; ++s) {
+                const int64_t j = knn[((size_t)b * S + p) * k + s];
+                float d[3], h1[8], w[16];
+                for (int a = 0; a < 3; ++a) d[a] = xyz[((size_t)b * 3 + a) * N + j] - sampled[((size_t)b * 3 + a) * S + p];
+                for (int o = 0; o < 8; ++o) {
+                    float v = ba[o];
+                    for (int a = 0; a < 3; ++a) v += Wa[o * 3 + a] * d[a];
+                    h1[o] = v > 0.0f ? v : 0.1f * v;
+                }
+                for (int o = 0; o < 16; ++o) {
+                    float v = bb[o];
+                    for (int i = 0; i < 8; ++i) v += Wb[o * 8 + i] * h1[i];
+                    w[o] = v > 0.0f ? v : 0.1f * v;
+                }
+                for (int o = 0; o < 16; ++o)
+                    for (int c = 0; c < Cf; ++c) {
+                        const float f = c < 3 ? xyz[((size_t)b * 3 + c) * N + j] : feat[((size_t)b * C + (c - 3)) * N + j];
+                        M[o * Cf + c] += w[o] * f;
+                    }
+            }
+            for (int o = 0; o < Cout; ++o) {
+                float v = bias[o];
+                for (int i = 0; i < 16 * Cf; ++i) v += L[(size_t)o * 16 * Cf + i] * M[i];
+                out[((size_t)b * Cout + o) * S + p] = v > 0.0f ? v : 0.1f * v;
+            }
+            free(M);
+        }
+}
+
+/* ---------------------------------------------------------------------------------------------------
  * f2 knn_interpolation — models/utils.py:140-156 (backwarp_3d :159-169 is this with xyz1+flow, -flow):
  * inverse-distance weights over the k nearest inputs, distance = ||x_j - q|| clamped at 1e-8, weights
  * normalised to sum 1, out[b,c,q] = sum_k w_k * feat[b,c,idx_k].  Indices are supplied by the caller. */

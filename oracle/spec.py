@@ -170,3 +170,18 @@ def knn_interpolate(input_xyz, input_feat, query_xyz, idx):
     out = np.empty((B, C, Q), np.float32)
     lib().orc_knn_interpolate(_p(input_xyz), _p(input_feat), _p(query_xyz), _p(idx), _p(out), B, C, M, Q, k)
     return out
+
+
+def pointconv_fwd(xyz, feat, sampled_xyz, knn, w):
+    """xyz [B,3,N], feat [B,C,N], sampled_xyz [B,3,S], knn [B,S,k]; w: dict Wa [8,3], ba, Wb [16,8], bb, L [out,16(C+3)],
+    bias -> [B,out,S] (models/pointconv.py:33-61 / :90-122)."""
+    xyz, feat, sampled_xyz, knn = _f32(xyz), _f32(feat), _f32(sampled_xyz), _i64(knn)
+    ws = {n: _f32(w[n]) for n in ("Wa", "ba", "Wb", "bb", "L", "bias")}
+    B, C, N = feat.shape
+    S, k = knn.shape[1], knn.shape[2]
+    cout = ws["L"].shape[0]
+    assert ws["L"].shape[1] == 16 * (C + 3)
+    out = np.empty((B, cout, S), np.float32)
+    lib().orc_pointconv_fwd(_p(xyz), _p(feat), _p(sampled_xyz), _p(knn), _p(ws["Wa"]), _p(ws["ba"]), _p(ws["Wb"]),
+                            _p(ws["bb"]), _p(ws["L"]), _p(ws["bias"]), _p(out), B, C, N, S, k, cout)
+    return out

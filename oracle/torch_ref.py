@@ -201,3 +201,17 @@ def knn_interpolation(input_xyz, input_features, query_xyz, k=3, knn_indices=Non
 def backwarp_3d(xyz1, xyz2, flow12, k=3):
     """models/utils.py:159-169."""
     return xyz2 + knn_interpolation(xyz1 + flow12, -flow12, xyz2, k)
+
+
+def pointconv(xyz, features, sampled_xyz, wts, k=16, knn=None):
+    """models/pointconv.py:33-61 (and :90-122 with sampled_xyz = xyz).  wts: Wa [8,3], ba, Wb [16,8], bb, L, bias."""
+    lrelu = lambda t: F.leaky_relu(t, 0.1)
+    nb, ns = xyz.shape[0], sampled_xyz.shape[2]
+    if knn is None:
+        knn = k_nearest_neighbor(xyz, sampled_xyz, k)
+    rel = batch_indexing_channel_first(xyz, knn) - sampled_xyz[:, :, :, None]                    # [B,3,S,k]
+    weights = _mlp(rel, [(wts['Wa'], wts['ba']), (wts['Wb'], wts['bb'])], lrelu).transpose(1, 2)   # [B,S,16,k]
+    cl = torch.cat([xyz, features], dim=1).transpose(1, 2)                                       # [B,N,C+3]
+    nbr = batch_indexing_channel_last(cl, knn)                                                   # [B,S,k,C+3]
+    mixed = torch.matmul(weights, nbr).reshape(nb, ns, -1)                                       # [B,S,16*(C+3)]
+    return lrelu(F.linear(mixed, wts['L'], wts['bias']).transpose(1, 2))

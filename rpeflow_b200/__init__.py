@@ -5,6 +5,7 @@ Public surface (same names as the reference, danqu130/RPEFlow):
   projection  batch_indexing_channel_{first,last}, grid_sample_wrapper, project_feat_with_nn_corr,
               knn_interpolation, backwarp_3d                                  (models/utils.py)
   pwc3d       Correlation3D, build_pc_pyramid                                 (models/pwc3d_core.py)
+  pointconv   PointConvDownSampling, PointConvNoSampling                      (models/pointconv.py)
   events      eventsToVoxel, eventsToVoxelInter                               (event_utils.py, dsec.py)
   install     install() — plug all of the above into an unmodified reference checkout
   stack       CostVolumeStack — replays one RPEFlow forward's hot-op census (bench.py's workload)
@@ -17,6 +18,7 @@ from .ops import (correlation2d, furthest_point_sampling, k_nearest_neighbor, sq
 from .projection import (batch_indexing_channel_first, batch_indexing_channel_last, grid_sample_wrapper,  # noqa: F401
                          project_feat_with_nn_corr, knn_interpolation, backwarp_3d)
 from .pwc3d import Correlation3D, build_pc_pyramid, correlation3d_forward  # noqa: F401
+from .pointconv import PointConvDownSampling, PointConvNoSampling, pointconv_forward  # noqa: F401
 from .events import eventsToVoxel, eventsToVoxelInter  # noqa: F401
 
 __version__ = "0.1.0"

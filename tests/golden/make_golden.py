@@ -150,6 +150,32 @@ def events():
          vox=obj.eventsToVoxelInter(d, 5, H, W, event_polarity=False))
 
 
+def pointconv():
+    from models.pointconv import PointConvDownSampling, PointConvNoSampling
+    for tag, cls, (B, C, cout, N, S, k) in (("down", PointConvDownSampling, (2, 13, 24, 120, 60, 16)),
+                                            ("nosample", PointConvNoSampling, (1, 32, 32, 70, 70, 16))):
+        torch.manual_seed(80)
+        mod = cls(C, cout, norm=None, k=k).eval()
+        gen = g(81)
+        xyz = torch.rand(B, 3, N, generator=gen) * 3
+        feat = torch.randn(B, C, N, generator=gen)
+        sd = mod.state_dict()
+        if cls is PointConvDownSampling:
+            sampled = xyz[:, :, :S].contiguous()
+            idx = k_nearest_neighbor(xyz, sampled, k)
+            with torch.no_grad():
+                out = mod(xyz, feat, sampled)
+        else:
+            sampled = xyz
+            idx = k_nearest_neighbor(xyz, xyz, k)
+            with torch.no_grad():
+                out = mod(xyz, feat, idx)
+        save("pointconv_" + tag, xyz=xyz, feat=feat, sampled=sampled, knn=idx, out=out,
+             w_Wa=sd["weight_net.convs.0.conv_fn.weight"][:, :, 0, 0], w_ba=sd["weight_net.convs.0.conv_fn.bias"],
+             w_Wb=sd["weight_net.convs.1.conv_fn.weight"][:, :, 0, 0], w_bb=sd["weight_net.convs.1.conv_fn.bias"],
+             w_L=sd["linear.weight"], w_bias=sd["linear.bias"])
+
+
 def interpolation():
     gen = g(70)
     xyz_in = torch.rand(2, 3, 300, generator=gen) * 4
@@ -167,6 +193,6 @@ def interpolation():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (corr2d, fps, knn, gathers, projection, corr3d, events, interpolation):
+    for fn in (corr2d, fps, knn, gathers, projection, corr3d, events, interpolation, pointconv):
         if not only or fn.__name__ in only:
             fn()

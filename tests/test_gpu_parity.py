@@ -529,3 +529,44 @@ def test_knn_interpolation_golden_and_levels(golden):
         np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
     with pytest.raises(RuntimeError):
         b200.knn_interpolation(xin, feat, xq, 3)                                              # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------------------------------------- PointConv (§8f rank 1)
+@pytest.mark.parametrize("precision,tol", [(2, 1e-4), (1, 5e-3)])
+@pytest.mark.parametrize("tag", ["down", "nosample"])
+def test_pointconv_golden(golden, tag, precision, tol):
+    g = golden("pointconv_" + tag)
+    w = {n[2:]: cu(g[n]) for n in g if n.startswith("w_")}
+    got = b200.pointconv_forward(cu(g["xyz"]), cu(g["feat"]), cu(g["sampled"]), cu(g["knn"]), w, precision)
+    scale = np.abs(g["out"]).max()
+    np.testing.assert_allclose(got.cpu().numpy(), g["out"], rtol=tol, atol=tol * scale)      # the reference's own output
+
+
+@pytest.mark.parametrize("C,cout,N,S", [(32, 32, 8192, 4096), (64, 64, 4096, 2048), (192, 192, 512, 256), (35, 64, 300, 300),
+                                         (0, 16, 100, 37)])
+def test_pointconv_modules_vs_oracle(C, cout, N, S):
+    gen = torch.Generator().manual_seed(C + N)
+    B = 2
+    xyz = torch.rand(B, 3, N, generator=gen) * 5
+    feat = torch.randn(B, C, N, generator=gen)
+    torch.manual_seed(7)
+    if S == N:
+        mod = b200.PointConvNoSampling(C, cout).to(DEV).eval()
+        with torch.no_grad():
+            got = mod(xyz.to(DEV), feat.to(DEV))
+        sampled = xyz
+    else:
+        mod = b200.PointConvDownSampling(C, cout).to(DEV).eval()
+        sampled = xyz[:, :, :S].contiguous()
+        with torch.no_grad():
+            got = mod(xyz.to(DEV), feat.to(DEV), sampled.to(DEV))
+    knn = b200.k_nearest_neighbor(xyz.to(DEV), sampled.to(DEV), 16).cpu()
+    w = {n: v.cpu() for n, v in b200.pointconv.pack_pointconv_weights(mod).items()}
+    want = spec.pointconv_fwd(xyz.numpy(), feat.numpy(), sampled.numpy(), knn.numpy(), {n: v.numpy() for n, v in w.items()})
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * scale)
+    assert set(mod.state_dict()) == {"weight_net.convs.0.conv_fn.weight", "weight_net.convs.0.conv_fn.bias",
+                                     "weight_net.convs.1.conv_fn.weight", "weight_net.convs.1.conv_fn.bias",
+                                     "linear.weight", "linear.bias"}
+    with pytest.raises(RuntimeError):
+        mod(xyz.to(DEV), feat.to(DEV).requires_grad_(True), *([] if S == N else [sampled.to(DEV)]))

@@ -142,3 +142,15 @@ def test_knn_interpolation_oracle_matches_reference_fixture(golden):
     ref = torch_ref.knn_interpolation(t(g["input_xyz"]), t(g["input_feat"]), t(g["query_xyz"]), 3)
     assert torch.equal(ref, t(g["out"]))
     assert torch.equal(torch_ref.backwarp_3d(t(g["input_xyz"]), t(g["xyz2"]), t(g["flow12"]), 3), t(g["backwarp"]))
+
+
+@pytest.mark.parametrize("tag", ["down", "nosample"])
+def test_pointconv_oracle_matches_reference_fixture(golden, tag):
+    """models/pointconv.py:33-61 / :90-122 (fixtures from the unmodified reference modules)."""
+    g = golden("pointconv_" + tag)
+    w = {n[2:]: g[n] for n in g if n.startswith("w_")}
+    got = spec.pointconv_fwd(g["xyz"], g["feat"], g["sampled"], g["knn"], w)
+    np.testing.assert_allclose(got, g["out"], rtol=1e-5, atol=1e-5)
+    t = lambda a: torch.from_numpy(a)
+    ref = torch_ref.pointconv(t(g["xyz"]), t(g["feat"]), t(g["sampled"]), {k: t(v) for k, v in w.items()}, 16, knn=t(g["knn"]))
+    assert torch.equal(ref, t(g["out"]))
