@@ -19,7 +19,7 @@ import sys
 
 import torch
 
-from . import events, ops, projection, pwc3d
+from . import events, ops, pointconv, projection, pwc3d
 from .shims import _correlation_cuda, _furthest_point_sampling_cuda, _k_nearest_neighbor_cuda
 
 _SHIMS = {
@@ -57,6 +57,31 @@ def _corr3d_forward(self, xyz1, feat1, xyz2, feat2, knn_indices_1in1=None):
     if knn_indices_1in1 is None:
         knn_indices_1in1 = ops.k_nearest_neighbor(input_xyz=xyz1, query_xyz=xyz1, k=self.k)
     return pwc3d.correlation3d_forward(xyz1, feat1, xyz2, feat2, pwc3d.pack_weights(self), knn12, knn_indices_1in1,
+                                       getattr(self, "b200_precision", 2))
+
+
+def _pointconv_fast_ok(self, features):
+    """The fused kernel covers the configuration RPEFlow uses; anything else (or autograd) keeps the reference forward."""
+    import torch.nn as nn
+    needs_graph = torch.is_grad_enabled() and (features.requires_grad or any(p.requires_grad for p in self.parameters()))
+    return (features.is_cuda and not needs_graph and self.k == 16 and isinstance(self.norm_fn, nn.Identity)
+            and isinstance(self.activation_fn, nn.LeakyReLU) and abs(self.activation_fn.negative_slope - 0.1) < 1e-12
+            and self.linear.out_features <= 256)
+
+
+def _pointconv_down_forward(self, xyz, features, sampled_xyz):
+    if not _pointconv_fast_ok(self, features):
+        return self._b200_reference_forward(xyz, features, sampled_xyz)
+    knn = ops.k_nearest_neighbor(xyz, sampled_xyz, self.k)
+    return pointconv.pointconv_forward(xyz, features, sampled_xyz, knn, pointconv.pack_pointconv_weights(self),
+                                       getattr(self, "b200_precision", 2))
+
+
+def _pointconv_nosample_forward(self, xyz, features, knn_indices=None):
+    if not _pointconv_fast_ok(self, features):
+        return self._b200_reference_forward(xyz, features, knn_indices)
+    knn = knn_indices[:, :, :self.k] if knn_indices is not None else ops.k_nearest_neighbor(xyz, xyz, self.k)
+    return pointconv.pointconv_forward(xyz, features, xyz, knn, pointconv.pack_pointconv_weights(self),
                                        getattr(self, "b200_precision", 2))
 
 
@@ -104,6 +129,11 @@ def patch_python_ops(patch_events=True):
         for name, fn in replaced.items():
             if hasattr(mod, name):
                 setattr(mod, name, fn)
+    pcm = importlib.import_module("models.pointconv")
+    for cls, fwd in ((pcm.PointConvDownSampling, _pointconv_down_forward), (pcm.PointConvNoSampling, _pointconv_nosample_forward)):
+        if not hasattr(cls, "_b200_reference_forward"):
+            cls._b200_reference_forward = cls.forward
+            cls.forward = fwd
     core = importlib.import_module("models.pwc3d_core")
     if not hasattr(core.Correlation3D, "_b200_reference_forward"):
         core.Correlation3D._b200_reference_forward = core.Correlation3D.forward

@@ -116,6 +116,13 @@ x = torch.rand(1, 3, 50)
 assert w.k_nearest_neighbor(x, x, 3).shape == (1, 50, 3)
 m = p3.Correlation3D(8, 8, k=4)
 assert m(x, torch.rand(1, 8, 50), x, torch.rand(1, 8, 50)).shape == (1, 8, 50)
+# widened rows (SURVEY 8f): PointConv, knn_interpolation, backwarp_3d, correlation2d are re-bound too and keep working on CPU
+import models.pointconv as pc, models.utils as mu
+assert hasattr(pc.PointConvDownSampling, '_b200_reference_forward') and hasattr(pc.PointConvNoSampling, '_b200_reference_forward')
+assert pc.PointConvNoSampling(8, 8)(x, torch.rand(1, 8, 50)).shape == (1, 8, 50)
+assert pc.PointConvDownSampling(8, 8)(x, torch.rand(1, 8, 50), x[:, :, :20]).shape == (1, 8, 20)
+assert mu.knn_interpolation(x, torch.rand(1, 5, 50), torch.rand(1, 3, 70)).shape == (1, 5, 70)
+assert core.correlation2d(torch.rand(1, 4, 8, 8), torch.rand(1, 4, 8, 8), 4).shape == (1, 81, 8, 8)
 print('SHIMS-OK')
 """
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
