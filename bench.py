@@ -316,7 +316,7 @@ def main():
     work = census_work(cfg)
     peak, peak_src = measured_peaks()
     c2 = per_op["corr2d_L1"]
-    # correlation2d() on the NCHW level-1 maps = one launch of corr2d_fwd_nchw_kernel (no permutes); timed alone here
+    # correlation2d() on the NCHW level-1 maps = one launch of corr2d_fwd_diag_kernel (no permutes); timed alone here
     # with an L2 flush between launches, and inside the step by the per-op brackets.
     f1, f2 = x["feat2d"][1][0], x["feat2d"][1][1]
     from rpeflow_b200 import ops
@@ -342,7 +342,7 @@ def main():
         with open(tpath) as f:
             per_pair = json.load(f).get(f"corr2d_fwd_L1_{cfg.name}_per_frame_pair")
             traffic = per_pair * B if per_pair else None
-    roofline = {"kernel": "corr2d_fwd_nchw_kernel (level 1: C=32, %dx%d, batch %d)" % (*cfg.level_hw(1), B),
+    roofline = {"kernel": "corr2d_fwd_diag_kernel (level 1: C=32, %dx%d, batch %d)" % (*cfg.level_hw(1), B),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": corr_bytes,
                 "launch_ms": corr_ms, "in_step_ms": c2["ms_per_step"]}

@@ -254,7 +254,11 @@ bool corr2d_nchw_eligible(const float* in1, const float* in2, const float* out, 
     return tiles > 0 && tiles < 0x7fffffff && tensor_map_encoder() != nullptr;
 }
 
+bool corr2d_diag_preferred(int W);                                              // corr2d_diag.cu
+cudaError_t corr2d_fwd_diag(const float* in1, const float* in2, float* out, int B, int C, int H, int W, cudaStream_t st);
+
 cudaError_t corr2d_fwd_nchw(const float* in1, const float* in2, float* out, int B, int C, int H, int W, cudaStream_t st) {
+    if (corr2d_diag_preferred(W)) return corr2d_fwd_diag(in1, in2, out, B, C, H, W, st);
     CUtensorMap m1, m2;
     if (!make_nchw_map(&m1, in1, B, C, H, W, N_AP, N_TH) || !make_nchw_map(&m2, in2, B, C, H, W, N_BP, N_HR))
         return cudaErrorInvalidValue;
