@@ -34,6 +34,10 @@ constexpr int KG_CELLS_MAX = 16384;     // cells per cloud (64 KB shared-memory 
 constexpr int KG_GMAX = 1024;           // cells per axis
 constexpr int KG_BUILD_THREADS = 1024;
 constexpr int KG_QUERY_THREADS = 128;
+#ifndef KG_STEP_N
+#define KG_STEP_N 4
+#endif
+constexpr int KG_STEP = KG_STEP_N;          // candidates per lane per lock-step iteration of the batched query (votes amortised)
 
 struct KnnGridParams {                  // 48 bytes per cloud, written by the build kernel
     float lo[3];
@@ -351,8 +355,9 @@ knn_grid_query_kernel(const float4* __restrict__ sorted_pts, const int* __restri
 // shared-memory batch instead; when some lane's batch is full (and at the end of the block) the whole warp sorts
 // its batches with a bitonic network and merges them into the lists — every lane busy, ~12*KMAX compare-swaps per
 // KMAX parked candidates.  A parked candidate that is no longer good enough simply loses the merge.
-// The warp walks the candidates in lock-step (each lane through its own rows of cells) so that it stays converged
-// for the drains.
+// The warp walks the candidates in lock-step (each lane through its own rows of cells, KG_STEP candidates per step
+// with their loads in flight together) so that it stays converged for the drains; a drain starts as soon as some
+// lane's batch could overflow in the next step.
 template <int D, int KMAX>
 __global__ void __launch_bounds__(KG_QUERY_THREADS)
 knn_grid_query_batched_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ cell_start,
@@ -380,7 +385,12 @@ knn_grid_query_batched_kernel(const float4* __restrict__ sorted_pts, const int* 
 #pragma unroll
             for (int s = 0; s < KMAX; ++s) L[s] = s < KMAX - k ? 0ull : KG_EMPTY;
         }
-        u64 thr = L[KMAX - 1];
+        // A pass only counts if its k-th best ends up strictly below the stop bound of this block; candidates at or
+        // beyond the bound cannot be part of such a result, so the bound also caps the parking threshold from the
+        // start (a pass that finds fewer than k candidates under it fails the test below and the block doubles).
+        const float bound = kg_bound<D>(s_p, q, r);
+        const u64 bkey = (u64)__float_as_uint(bound) << 32;
+        u64 thr = L[KMAX - 1] < bkey ? L[KMAX - 1] : bkey;
         // rows of cells: the query's own row first (it fills the list with near points, so most later candidates
         // fail the threshold test), then the others in storage order
         int y = y0, z = done ? z1 + 1 : z0, c = 0, e = 0, nb = 0;
@@ -399,19 +409,28 @@ knn_grid_query_batched_kernel(const float4* __restrict__ sorted_pts, const int* 
             }
             const bool active = c < e;
             if (!__any_sync(FULL, active)) break;
-            if (active) {
-                const u64 key = kg_key<D>(q, __ldg(sorted_pts + c));
-                ++c;
-                if (key < thr) s_batch[nb++][threadIdx.x] = key;
+            {                                            // up to KG_STEP candidates of this lane's row per warp step
+                const int n = active ? min(e - c, KG_STEP) : 0;
+                float4 pt[KG_STEP];
+#pragma unroll
+                for (int j = 0; j < KG_STEP; ++j)
+                    if (j < n) pt[j] = __ldg(sorted_pts + c + j);
+#pragma unroll
+                for (int j = 0; j < KG_STEP; ++j)
+                    if (j < n) {
+                        const u64 key = kg_key<D>(q, pt[j]);
+                        if (key < thr) s_batch[nb++][threadIdx.x] = key;
+                    }
+                c += n;
             }
-            if (__any_sync(FULL, nb == KMAX)) {
+            if (__any_sync(FULL, nb > KMAX - KG_STEP)) {  // the next step may park KG_STEP more
                 u64 batch[KMAX];
 #pragma unroll
                 for (int j = 0; j < KMAX; ++j) batch[j] = j < nb ? s_batch[j][threadIdx.x] : ~0ull;
                 kg_bitonic_sort<KMAX>(batch);
                 kg_merge_sorted<KMAX>(L, batch);
                 nb = 0;
-                thr = L[KMAX - 1];
+                thr = L[KMAX - 1] < bkey ? L[KMAX - 1] : bkey;
             }
         }
         if (__any_sync(FULL, nb > 0)) {
@@ -424,7 +443,7 @@ knn_grid_query_batched_kernel(const float4* __restrict__ sorted_pts, const int* 
         if (!done) {
             const bool whole = x0 == 0 && y0 == 0 && z0 == 0 && x1 == Gx - 1 && y1 == Gy - 1 && z1 == Gz - 1;
             const float kth = __uint_as_float((unsigned)(L[KMAX - 1] >> 32));
-            done = whole || kth < kg_bound<D>(s_p, q, r);
+            done = whole || kth < bound;
         }
         if (__all_sync(FULL, done)) break;
     }
