@@ -61,6 +61,22 @@ B200_API int b200_corr2d_fwd(const float* in1_nhwc, const float* in2_nhwc, float
 B200_API int b200_corr2d_fwd_nchw(const float* in1_nchw, const float* in2_nchw, float* out_nchw,
                          int B, int C, int H, int W, int md, b200_stream_t stream);
 
+/* f3  a1 with the caller's activation fused: leaky_relu(correlation2d(f1, f2_warp, md), slope),
+ * models/RPEFlow_core.py:362 — the activation is the epilogue of the same kernels, no extra pass over the 81 planes.
+ * negative_slope in [0,1]; 1 is the identity (== b200_corr2d_fwd_nchw).  Same limits as b200_corr2d_fwd_nchw.
+ */
+B200_API int b200_corr2d_fwd_nchw_leaky(const float* in1_nchw, const float* in2_nchw, float* out_nchw,
+                               int B, int C, int H, int W, int md, float negative_slope, b200_stream_t stream);
+
+/* f3  backwarp_2d with padding_mode='border' (models/utils.py:186-198; caller RPEFlow_core.py:351): the producer of
+ * in2 for the call above at every level but the coarsest.
+ *   x : [B,C,H,W] NCHW fp32;  flow : [B,2,H,W] (x then y displacement, pixels)  ->  out : [B,C,H,W]
+ *   out[b,c,y,x] = bilinear(x[b,c], (x + flow[b,0,y,x], y + flow[b,1,y,x])), align_corners=True, coordinates clamped to
+ *   the image (border).  Coordinates take the reference's normalise / un-normalise round trip in fp32.
+ */
+B200_API int b200_backwarp2d(const float* x_nchw, const float* flow, float* out_nchw,
+                    int B, int C, int H, int W, b200_stream_t stream);
+
 /* a2  backward of a1.
  * Replaces: correlation.cpp:24-35 (correlation_backward_cuda) + correlation_backward_kernel.cu:4-89;
  *           binding `_correlation_backward_cuda` (correlation.cpp:40), called from wrapper.py:31.

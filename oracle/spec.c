@@ -286,6 +286,26 @@ ORC_API void orc_grid_sample_pts(const float* feat, const float* xy, float* out,
             }
 }
 
+/* f3 backwarp_2d, padding_mode='border' — models/utils.py:186-198: grid = mesh_grid + flow, normalised as above,
+ * then F.grid_sample(align_corners=True, padding_mode='border'): un-normalise, clamp to [0, size-1], blend the
+ * in-bounds taps (a clamped x0 = W-1 leaves x1 = W out of bounds, weight 0). */
+ORC_API void orc_backwarp2d_border(const float* x, const float* flow, float* out, int B, int C, int H, int W) {
+    const size_t HW = (size_t)H * W;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int c = 0; c < C; ++c)
+            for (int py = 0; py < H; ++py)
+                for (int px = 0; px < W; ++px) {
+                    const size_t p = (size_t)py * W + px;
+                    float gx = (float)px + flow[((size_t)b * 2 + 0) * HW + p];
+                    float gy = (float)py + flow[((size_t)b * 2 + 1) * HW + p];
+                    float ix = renorm_coord(gx, W), iy = renorm_coord(gy, H);
+                    ix = fminf((float)(W - 1), fmaxf(ix, 0.0f));
+                    iy = fminf((float)(H - 1), fmaxf(iy, 0.0f));
+                    out[((size_t)b * C + c) * HW + p] = bilinear_zero(x + ((size_t)b * C + c) * HW, H, W, ix, iy);
+                }
+}
+
 /* a8 project_feat_with_nn_corr — models/utils.py:297-317 with nn_indices given. */
 ORC_API void orc_project_nn_corr(const float* xy, const float* feat2d, const float* feat3d,
                                  const int64_t* nn, float* out,

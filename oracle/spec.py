@@ -111,6 +111,15 @@ def grid_sample_pts(feat, xy):
     return out
 
 
+def backwarp2d_border(x, flow):
+    """x [B,C,H,W], flow [B,2,H,W] -> [B,C,H,W] (models/utils.py:186-198, padding_mode='border')."""
+    x, flow = _f32(x), _f32(flow)
+    B, C, H, W = x.shape
+    out = np.empty_like(x)
+    lib().orc_backwarp2d_border(_p(x), _p(flow), _p(out), B, C, H, W)
+    return out
+
+
 def project_nn_corr(xy, feat2d, feat3d, nn):
     xy, feat2d, feat3d, nn = _f32(xy), _f32(feat2d), _f32(feat3d), _i64(nn)
     B, C2, H, W = feat2d.shape

@@ -203,6 +203,25 @@ def backwarp_3d(xyz1, xyz2, flow12, k=3):
     return xyz2 + knn_interpolation(xyz1 + flow12, -flow12, xyz2, k)
 
 
+# ------------------------------------------------------------------ f3  models/utils.py:186-198, RPEFlow_core.py:351,362
+def backwarp_2d(x, flow12, padding_mode='border'):
+    """x [B,C,H,W] sampled at pixel + flow12 [B,2,H,W]; grid normalised exactly as norm_grid does."""
+    nb, _, h, w = x.shape
+    xs = torch.arange(0, w, dtype=torch.float32)[None, None, :].expand(nb, h, w)
+    ys = torch.arange(0, h, dtype=torch.float32)[None, :, None].expand(nb, h, w)
+    g = torch.stack([xs, ys], 1) + flow12
+    gn = torch.zeros_like(g)
+    gn[:, 0] = 2.0 * g[:, 0] / (w - 1) - 1.0
+    gn[:, 1] = 2.0 * g[:, 1] / (h - 1) - 1.0
+    return F.grid_sample(x, gn.permute(0, 2, 3, 1), padding_mode=padding_mode, align_corners=True)
+
+
+def warp_correlate(feat1, feat2, flow, md=4, negative_slope=0.1):
+    """leaky_relu(correlation2d(feat1, backwarp_2d(feat2, flow, 'border'), md), 0.1) — RPEFlow_core.py:351 + :362."""
+    warped = feat2 if flow is None else backwarp_2d(feat2, flow, 'border')
+    return F.leaky_relu(correlation2d(feat1, warped, md), negative_slope)
+
+
 def pointconv(xyz, features, sampled_xyz, wts, k=16, knn=None):
     """models/pointconv.py:33-61 (and :90-122 with sampled_xyz = xyz).  wts: Wa [8,3], ba, Wb [16,8], bb, L, bias."""
     lrelu = lambda t: F.leaky_relu(t, 0.1)

@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200flow.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_i, c_i64, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
 
@@ -35,6 +35,8 @@ SIGNATURES = {
     "b200_last_error": (ctypes.c_char_p, []),
     "b200_corr2d_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "b200_corr2d_fwd_nchw": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "b200_corr2d_fwd_nchw_leaky": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, ctypes.c_float, c_p]),
+    "b200_backwarp2d": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "b200_corr2d_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "b200_fps": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "b200_knn": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),

@@ -84,7 +84,7 @@ __device__ __forceinline__ void corr2d_diag_consume(DAcc (&acc)[ROWS][D_P], uint
 
 // Stores one output row of a thread (6 px x 9 column shifts) and clears the accumulators.
 __device__ __forceinline__ void corr2d_diag_store(DAcc (&acc)[D_P], float* __restrict__ o, size_t plane, float inv_c,
-                                                  bool even, bool ok4, bool ok2) {
+                                                  float slope, bool even, bool ok4, bool ok2) {
     float lo[D_P][4], hi[D_P][4];
 #pragma unroll
     for (int i = 0; i < D_P; ++i)
@@ -100,7 +100,8 @@ __device__ __forceinline__ void corr2d_diag_store(DAcc (&acc)[D_P], float* __res
             float t;
             if ((i & 1) == 0) t = d == 8 ? acc[i].s : ((d & 1) ? hi[i][d >> 1] : lo[i][d >> 1]);
             else              t = d == 0 ? acc[i].s : ((d & 1) ? lo[i][(d - 1) >> 1] : hi[i][(d - 1) >> 1]);
-            v[i] = t * inv_c;
+            t *= inv_c;
+            v[i] = fmaxf(t, t * slope);              // leaky_relu epilogue (slope 1 = none): RPEFlow_core.py:362
         }
         const float4 f4 = even ? make_float4(v[0], v[1], v[2], v[3]) : make_float4(v[2], v[3], v[4], v[5]);
         const float2 f2 = even ? make_float2(v[4], v[5]) : make_float2(v[0], v[1]);
@@ -120,7 +121,7 @@ __device__ __forceinline__ void corr2d_diag_store(DAcc (&acc)[D_P], float* __res
 template <int ROWS>
 __device__ __forceinline__ void corr2d_diag_consumer(uint32_t base, uint32_t bar_full, uint32_t bar_empty, float* __restrict__ out,
                                                      int H, int W, int tiles_x, int per_img, int num_tiles, int nchunks,
-                                                     float inv_c, int warp, int lane) {
+                                                     float inv_c, float slope, int warp, int lane) {
     const int rp = lane & 3, strip = lane >> 2;
     // in2 halo row offset o of this warp; first in1 row of the thread inside its row pair; dy index of acc[0]
     const int o = warp < 8 ? warp + 1 : (warp == 8 ? 0 : 9);
@@ -160,14 +161,14 @@ __device__ __forceinline__ void corr2d_diag_consumer(uint32_t base, uint32_t bar
             const int y = ty * D_TH + arow + rr;
             float* op = out + ((size_t)b * (D_ND * D_ND) + (size_t)(dy0 - rr) * D_ND) * plane + (size_t)y * W + x;
             const bool yok = y < H;
-            corr2d_diag_store(acc[rr], op, plane, inv_c, even, yok && ok4, yok && ok2);
+            corr2d_diag_store(acc[rr], op, plane, inv_c, slope, even, yok && ok4, yok && ok2);
         }
     }
 }
 
 __global__ void __launch_bounds__(D_THREADS, 1)
 corr2d_fwd_diag_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
-                       float* __restrict__ out, int C, int H, int W, int tiles_x, int tiles_y, int num_tiles, float inv_c) {
+                       float* __restrict__ out, int C, int H, int W, int tiles_x, int tiles_y, int num_tiles, float inv_c, float slope) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_full = base + D_NSTAGE * D_STAGE;
@@ -210,9 +211,9 @@ corr2d_fwd_diag_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         return;
     }
     if (warp < 8)
-        corr2d_diag_consumer<2>(base, bar_full, bar_empty, out, H, W, tiles_x, per_img, num_tiles, nchunks, inv_c, warp, lane);
+        corr2d_diag_consumer<2>(base, bar_full, bar_empty, out, H, W, tiles_x, per_img, num_tiles, nchunks, inv_c, slope, warp, lane);
     else
-        corr2d_diag_consumer<1>(base, bar_full, bar_empty, out, H, W, tiles_x, per_img, num_tiles, nchunks, inv_c, warp, lane);
+        corr2d_diag_consumer<1>(base, bar_full, bar_empty, out, H, W, tiles_x, per_img, num_tiles, nchunks, inv_c, slope, warp, lane);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
@@ -238,7 +239,8 @@ bool corr2d_diag_preferred(int W) {
     return w48 <= 1.2 * w32;
 }
 
-cudaError_t corr2d_fwd_diag(const float* in1, const float* in2, float* out, int B, int C, int H, int W, cudaStream_t st) {
+cudaError_t corr2d_fwd_diag(const float* in1, const float* in2, float* out, int B, int C, int H, int W, float slope,
+                            cudaStream_t st) {
     CUtensorMap m1, m2;
     if (!make_diag_map(&m1, in1, B, C, H, W, D_TH) || !make_diag_map(&m2, in2, B, C, H, W, D_HR)) return cudaErrorInvalidValue;
     const int tiles_x = ceil_div(W, D_TW), tiles_y = ceil_div(H, D_TH);
@@ -246,7 +248,7 @@ cudaError_t corr2d_fwd_diag(const float* in1, const float* in2, float* out, int 
     cudaError_t e = cudaFuncSetAttribute(corr2d_fwd_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SMEM);
     if (e != cudaSuccess) return e;
     const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-    corr2d_fwd_diag_kernel<<<grid, D_THREADS, D_SMEM, st>>>(m1, m2, out, C, H, W, tiles_x, tiles_y, num_tiles, 1.0f / (float)C);
+    corr2d_fwd_diag_kernel<<<grid, D_THREADS, D_SMEM, st>>>(m1, m2, out, C, H, W, tiles_x, tiles_y, num_tiles, 1.0f / (float)C, slope);
     return cudaGetLastError();
 }
 

@@ -90,7 +90,7 @@ __device__ __forceinline__ void corr2d_nchw_consume(NAcc (&acc)[N_P], uint32_t p
 
 __global__ void __launch_bounds__(N_THREADS, 1)   // 11 warps are allocated as 12: 168 registers per thread
 corr2d_fwd_nchw_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
-                       float* __restrict__ out, int C, int H, int W, int tiles_x, int tiles_y, int num_tiles, float inv_c) {
+                       float* __restrict__ out, int C, int H, int W, int tiles_x, int tiles_y, int num_tiles, float inv_c, float slope) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_full = base + N_NSTAGE * N_STAGE + N_COMB_BYTES;
@@ -215,7 +215,8 @@ corr2d_fwd_nchw_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                 float t;
                 if ((i & 1) == 0) t = d == 8 ? acc[i].s : ((d & 1) ? hi[i][d >> 1] : lo[i][d >> 1]);
                 else              t = d == 0 ? acc[i].s : ((d & 1) ? lo[i][(d - 1) >> 1] : hi[i][(d - 1) >> 1]);
-                v[i] = t * inv_c;
+                t *= inv_c;
+                v[i] = fmaxf(t, t * slope);              // leaky_relu epilogue (slope 1 = none): RPEFlow_core.py:362
             }
 #pragma unroll
             for (int m = 0; m < N_P / 4; ++m)
@@ -255,10 +256,12 @@ bool corr2d_nchw_eligible(const float* in1, const float* in2, const float* out, 
 }
 
 bool corr2d_diag_preferred(int W);                                              // corr2d_diag.cu
-cudaError_t corr2d_fwd_diag(const float* in1, const float* in2, float* out, int B, int C, int H, int W, cudaStream_t st);
+cudaError_t corr2d_fwd_diag(const float* in1, const float* in2, float* out, int B, int C, int H, int W, float slope,
+                            cudaStream_t st);
 
-cudaError_t corr2d_fwd_nchw(const float* in1, const float* in2, float* out, int B, int C, int H, int W, cudaStream_t st) {
-    if (corr2d_diag_preferred(W)) return corr2d_fwd_diag(in1, in2, out, B, C, H, W, st);
+cudaError_t corr2d_fwd_nchw(const float* in1, const float* in2, float* out, int B, int C, int H, int W, float slope,
+                            cudaStream_t st) {
+    if (corr2d_diag_preferred(W)) return corr2d_fwd_diag(in1, in2, out, B, C, H, W, slope, st);
     CUtensorMap m1, m2;
     if (!make_nchw_map(&m1, in1, B, C, H, W, N_AP, N_TH) || !make_nchw_map(&m2, in2, B, C, H, W, N_BP, N_HR))
         return cudaErrorInvalidValue;
@@ -267,25 +270,36 @@ cudaError_t corr2d_fwd_nchw(const float* in1, const float* in2, float* out, int 
     cudaError_t e = cudaFuncSetAttribute(corr2d_fwd_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)N_SMEM);
     if (e != cudaSuccess) return e;
     const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-    corr2d_fwd_nchw_kernel<<<grid, N_THREADS, N_SMEM, st>>>(m1, m2, out, C, H, W, tiles_x, tiles_y, num_tiles, 1.0f / (float)C);
+    corr2d_fwd_nchw_kernel<<<grid, N_THREADS, N_SMEM, st>>>(m1, m2, out, C, H, W, tiles_x, tiles_y, num_tiles, 1.0f / (float)C, slope);
     return cudaGetLastError();
 }
 
 }  // namespace b200
 
-extern "C" int b200_corr2d_fwd_nchw(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int md,
-                                    b200_stream_t stream) {
+static int corr2d_fwd_nchw_entry(const char* who, const float* in1, const float* in2, float* out, int B, int C, int H, int W,
+                                 int md, float slope, b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(in1 && in2 && out, "b200_corr2d_fwd_nchw: null pointer");
-    B200_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "b200_corr2d_fwd_nchw: bad sizes B=%d C=%d H=%d W=%d", B, C, H, W);
-    B200_REQUIRE(md >= 1 && md <= 4, "b200_corr2d_fwd_nchw: max_displacement must be in [1,4] (got %d)", md);
+    B200_REQUIRE(in1 && in2 && out, "%s: null pointer", who);
+    B200_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "%s: bad sizes B=%d C=%d H=%d W=%d", who, B, C, H, W);
+    B200_REQUIRE(md >= 1 && md <= 4, "%s: max_displacement must be in [1,4] (got %d)", who, md);
+    B200_REQUIRE(slope >= 0.0f && slope <= 1.0f, "%s: negative_slope must be in [0,1] (got %g)", who, (double)slope);
     if (B == 0) return B200_OK;
     if (!corr2d_nchw_eligible(in1, in2, out, B, C, H, W, md)) {
-        set_error("b200_corr2d_fwd_nchw: needs md=4, W %% 4 == 0 and 16-byte aligned pointers (permute to NHWC and call "
-                  "b200_corr2d_fwd otherwise)");
+        set_error("%s: needs md=4, W %% 4 == 0 and 16-byte aligned pointers (permute to NHWC and call b200_corr2d_fwd otherwise)",
+                  who);
         return B200_ENOSUP;
     }
-    const cudaError_t e = corr2d_fwd_nchw(in1, in2, out, B, C, H, W, as_stream(stream));
-    if (e != cudaSuccess) return cuda_fail(e, "b200_corr2d_fwd_nchw");
+    const cudaError_t e = corr2d_fwd_nchw(in1, in2, out, B, C, H, W, slope, as_stream(stream));
+    if (e != cudaSuccess) return cuda_fail(e, who);
     return B200_OK;
+}
+
+extern "C" int b200_corr2d_fwd_nchw(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int md,
+                                    b200_stream_t stream) {
+    return corr2d_fwd_nchw_entry("b200_corr2d_fwd_nchw", in1, in2, out, B, C, H, W, md, 1.0f, stream);
+}
+
+extern "C" int b200_corr2d_fwd_nchw_leaky(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int md,
+                                          float negative_slope, b200_stream_t stream) {
+    return corr2d_fwd_nchw_entry("b200_corr2d_fwd_nchw_leaky", in1, in2, out, B, C, H, W, md, negative_slope, stream);
 }

@@ -149,6 +149,58 @@ grid_sample_pts_kernel(const float* __restrict__ feat, const float* __restrict__
     }
 }
 
+// f3: backwarp_2d (models/utils.py:186-198) with padding_mode='border': out[b,c,p] = bilinear(x[b,c], pixel p + flow[b,:,p]).
+// The grid takes the reference's round trip (mesh + flow, 2*g/(W-1)-1, then grid_sample's ((g+1)/2)*(W-1)), is then
+// clamped to [0, size-1] (ATen clip_coordinates) and sampled like a7; a clamped x0 = W-1 leaves the right tap outside
+// the image with weight 0, exactly as ATen's within_bounds test does.
+__device__ __forceinline__ Taps make_taps_border(float gx, float gy, int H, int W) {
+    float ix = renorm_coord(gx, W), iy = renorm_coord(gy, H);
+    ix = fminf((float)(W - 1), fmaxf(ix, 0.0f));
+    iy = fminf((float)(H - 1), fmaxf(iy, 0.0f));
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float wx1 = ix - fx, wy1 = iy - fy, wx0 = (fx + 1.0f) - ix, wy0 = (fy + 1.0f) - iy;
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;          // clamped: always finite and in range
+    const bool vx1 = x1 < W, vy1 = y1 < H;
+    Taps t;
+    t.o00 = y0 * W + x0;                 t.w00 = wx0 * wy0;
+    t.o01 = vx1 ? y0 * W + x1 : -1;      t.w01 = wx1 * wy0;
+    t.o10 = vy1 ? y1 * W + x0 : -1;      t.w10 = wx0 * wy1;
+    t.o11 = (vy1 && vx1) ? y1 * W + x1 : -1; t.w11 = wx1 * wy1;
+    return t;
+}
+
+// grid: (ceil(HW/128), csplit, B); two lanes per pixel as in grid_sample_pts_kernel
+__global__ void __launch_bounds__(256)
+backwarp2d_border_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
+                         int C, int H, int W) {
+    const int b = blockIdx.z;
+    const int side = threadIdx.x & 1;
+    const int HW = H * W;
+    const int p = blockIdx.x * 128 + (threadIdx.x >> 1);
+    const bool ok = p < HW;
+    Taps t = {-1, -1, -1, -1, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (ok) {
+        const float gx = __fadd_rn((float)(p % W), __ldg(flow + ((size_t)b * 2 + 0) * HW + p));    // mesh_grid + flow12
+        const float gy = __fadd_rn((float)(p / W), __ldg(flow + ((size_t)b * 2 + 1) * HW + p));
+        t = make_taps_border(gx, gy, H, W);
+    }
+    const HalfTaps h = half_taps(t, side);
+    const float* f = x + (size_t)b * C * HW;
+    float* o = out + (size_t)b * C * HW + p;
+    int c = blockIdx.y * 2;
+    for (; c + 1 < C; c += gridDim.y * 2) {
+        float v0 = half_blend(f + (size_t)c * HW, h), v1 = half_blend(f + (size_t)(c + 1) * HW, h);
+        v0 += __shfl_xor_sync(FULL, v0, 1);
+        v1 += __shfl_xor_sync(FULL, v1, 1);
+        if (ok) o[(size_t)(c + side) * HW] = side ? v1 : v0;
+    }
+    if (c < C) {
+        float v0 = half_blend(f + (size_t)c * HW, h);
+        v0 += __shfl_xor_sync(FULL, v0, 1);
+        if (ok && side == 0) o[(size_t)c * HW] = v0;
+    }
+}
+
 // a8, pass 1: S[b,n,c] = bilinear(feat2d[b,c], xy[b,:,n])  (point-major scratch).  Block = 16 points; compute: a warp
 // owns 4 of every 32 channels, lanes = 16 points x 2 tap sides (see half_taps); write: lane = channel (contiguous in S).
 __global__ void __launch_bounds__(256)
@@ -345,6 +397,20 @@ extern "C" int b200_grid_sample_pts(const float* feat, const float* xy, float* o
     dim3 grid(ceil_div(N, 128), csplit, B);
     grid_sample_pts_kernel<<<grid, 256, 0, as_stream(stream)>>>(feat, xy, out, C, H, W, N);
     B200_LAUNCH_CHECK("b200_grid_sample_pts");
+    return B200_OK;
+}
+
+extern "C" int b200_backwarp2d(const float* x, const float* flow, float* out, int B, int C, int H, int W, b200_stream_t stream) {
+    using namespace b200;
+    B200_REQUIRE(x && flow && out, "b200_backwarp2d: null pointer");
+    B200_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1, "b200_backwarp2d: bad sizes");
+    B200_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, "b200_backwarp2d: plane or batch too large");
+    if (B == 0 || C == 0) return B200_OK;
+    const int64_t HW = (int64_t)H * W;
+    int csplit = pick_csplit(HW * 2, B, (C + 1) / 2);
+    dim3 grid(ceil_div(HW, 128), csplit, B);
+    backwarp2d_border_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, flow, out, C, H, W);
+    B200_LAUNCH_CHECK("b200_backwarp2d");
     return B200_OK;
 }
 

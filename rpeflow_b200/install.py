@@ -118,8 +118,15 @@ def patch_python_ops(patch_events=True):
                                                                       or xyz2.requires_grad)):
             return ref_backwarp(xyz1, xyz2, flow12, k)
         return projection.backwarp_3d(xyz1, xyz2, flow12, k)
+    ref_backwarp_2d = mutils.backwarp_2d
+
+    def backwarp_2d(x, flow12, padding_mode):
+        if not x.is_cuda or padding_mode != "border" or (torch.is_grad_enabled() and (x.requires_grad or flow12.requires_grad)):
+            return ref_backwarp_2d(x, flow12, padding_mode)
+        return projection.backwarp_2d(x, flow12, padding_mode)
     replaced["knn_interpolation"] = knn_interpolation
     replaced["backwarp_3d"] = backwarp_3d
+    replaced["backwarp_2d"] = backwarp_2d
     for modname in ("models.utils", "models.RPEFlow_core", "models.pwc2d_core", "models.pwc3d_core", "models.pointconv",
                     "models.losses3d", "models.RPEFlow", "models.csrc", "models.csrc.wrapper"):
         try:

@@ -142,6 +142,27 @@ def _no_fallback(name, *tensors):
             raise RuntimeError(f"rpeflow_b200.{name}: CUDA tensors required — this build has no CPU/torch fallback")
 
 
+def _correlation2d_nchw(input1, input2, max_displacement, negative_slope):
+    """The single-pass NCHW route (b200_corr2d_fwd_nchw[_leaky]); None when the call is outside its limits."""
+    needs_grad = torch.is_grad_enabled() and (input1.requires_grad or input2.requires_grad)
+    if needs_grad or int(max_displacement) != 4 or input1.dim() != 4 or input1.shape != input2.shape \
+            or input1.shape[3] % 4 != 0:
+        return None
+    a, b = input1.contiguous().float(), input2.contiguous().float()
+    B, C, H, W = a.shape
+    out = torch.empty((B, 81, H, W), dtype=torch.float32, device=a.device)
+    if a.data_ptr() % 16 or b.data_ptr() % 16 or out.data_ptr() % 16:
+        return None
+    with torch.cuda.device(a.device):
+        if negative_slope is None:
+            check(lib.b200_corr2d_fwd_nchw(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, 4, _stream(a)),
+                  "b200_corr2d_fwd_nchw")
+        else:
+            check(lib.b200_corr2d_fwd_nchw_leaky(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, 4,
+                                                 float(negative_slope), _stream(a)), "b200_corr2d_fwd_nchw_leaky")
+    return out
+
+
 def correlation2d(input1, input2, max_displacement, cpp_impl=True):
     """input1, input2 [B,C,H,W] -> [B,(2md+1)^2,H,W] (wrapper.py:55-72). cpp_impl is accepted and ignored.
 
@@ -149,20 +170,47 @@ def correlation2d(input1, input2, max_displacement, cpp_impl=True):
     volume is computed straight from the NCHW maps (b200_corr2d_fwd_nchw): the wrapper's two permutes are gone.
     Otherwise: permute to NHWC and go through CorrelationFunction exactly as wrapper.py:68-70 does."""
     _no_fallback("correlation2d", input1, input2)
-    needs_grad = torch.is_grad_enabled() and (input1.requires_grad or input2.requires_grad)
-    if not needs_grad and int(max_displacement) == 4 and input1.dim() == 4 and input1.shape == input2.shape \
-            and input1.shape[3] % 4 == 0:
-        a, b = input1.contiguous().float(), input2.contiguous().float()
-        B, C, H, W = a.shape
-        out = torch.empty((B, 81, H, W), dtype=torch.float32, device=a.device)
-        if a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0:
-            with torch.cuda.device(a.device):
-                check(lib.b200_corr2d_fwd_nchw(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, 4, _stream(a)),
-                      "b200_corr2d_fwd_nchw")
-            return out
+    out = _correlation2d_nchw(input1, input2, max_displacement, None)
+    if out is not None:
+        return out
     input1 = input1.permute(0, 2, 3, 1).contiguous().float()
     input2 = input2.permute(0, 2, 3, 1).contiguous().float()
     return CorrelationFunction.apply(input1, input2, max_displacement)
+
+
+def correlation2d_leaky(input1, input2, max_displacement, negative_slope=0.1):
+    """leaky_relu(correlation2d(input1, input2, md), negative_slope) — the expression of RPEFlow_core.py:362 — with the
+    activation as the epilogue of the correlation kernel.  Outside the single-pass route's limits
+    (autograd, md != 4, W % 4 != 0) it is the two-op composition."""
+    _no_fallback("correlation2d_leaky", input1, input2)
+    if not 0.0 <= float(negative_slope) <= 1.0:
+        raise RuntimeError("rpeflow_b200.correlation2d_leaky: negative_slope must be in [0, 1]")
+    out = _correlation2d_nchw(input1, input2, max_displacement, negative_slope)
+    if out is not None:
+        return out
+    return torch.nn.functional.leaky_relu(correlation2d(input1, input2, max_displacement), float(negative_slope))
+
+
+def warp_correlate(feat1_2d, feat2_2d, flow_2d, max_displacement=4, negative_slope=0.1, l2_budget_bytes=48 << 20):
+    """RPEFlow_core.py:351+362 as one call: leaky_relu(correlation2d(feat1, backwarp_2d(feat2, flow, 'border'), md), slope).
+
+    The warped map is an intermediate nobody else reads, so the batch is walked in chunks whose warped maps fit the
+    L2 budget: each chunk's backwarp output is still L2-resident when the correlation's TMA loads ask for it and the
+    map never makes the round trip through HBM.  flow_2d None = the coarsest level (no warp, RPEFlow_core.py:346)."""
+    from .projection import backwarp_2d
+    _no_fallback("warp_correlate", feat1_2d, feat2_2d)
+    if flow_2d is None:
+        return correlation2d_leaky(feat1_2d, feat2_2d, max_displacement, negative_slope)
+    B = feat1_2d.shape[0]
+    per_sample = feat2_2d[0].numel() * 4
+    chunk = max(1, min(B, int(l2_budget_bytes // max(per_sample, 1))))
+    if chunk >= B:
+        return correlation2d_leaky(feat1_2d, backwarp_2d(feat2_2d, flow_2d, "border"), max_displacement, negative_slope)
+    outs = []
+    for i in range(0, B, chunk):
+        warped = backwarp_2d(feat2_2d[i:i + chunk], flow_2d[i:i + chunk], "border")
+        outs.append(correlation2d_leaky(feat1_2d[i:i + chunk], warped, max_displacement, negative_slope))
+    return torch.cat(outs, dim=0)
 
 
 def furthest_point_sampling(xyz, n_samples, cpp_impl=True):

@@ -10,7 +10,7 @@ import torch
 
 from ._lib import check, lib
 
-__all__ = ["batch_indexing_channel_first", "batch_indexing_channel_last", "grid_sample_wrapper",
+__all__ = ["batch_indexing_channel_first", "batch_indexing_channel_last", "grid_sample_wrapper", "backwarp_2d",
            "project_feat_with_nn_corr", "knn_interpolation", "backwarp_3d"]
 
 
@@ -78,6 +78,26 @@ def grid_sample_wrapper(feat_2d, xy):
     with torch.cuda.device(feat.device):
         check(lib.b200_grid_sample_pts(feat.data_ptr(), pts.data_ptr(), out.data_ptr(), B, C, H, W, N,
                                        _stream(feat)), "b200_grid_sample_pts")
+    return out
+
+
+def backwarp_2d(x, flow12, padding_mode="border"):
+    """x [B,C,H,W], flow12 [B,2,H,W] -> x sampled at (pixel + flow), bilinear, align_corners=True (models/utils.py:186-198).
+    The model only ever passes padding_mode='border' (RPEFlow_core.py:351); other modes are not built."""
+    if not (x.is_cuda and flow12.is_cuda):
+        raise RuntimeError("rpeflow_b200.backwarp_2d: CUDA tensors required — no CPU/torch fallback")
+    if padding_mode != "border":
+        raise RuntimeError("rpeflow_b200.backwarp_2d: only padding_mode='border' is built (the mode RPEFlow uses)")
+    assert x.shape[-2:] == flow12.shape[-2:]                       # models/utils.py:193
+    if torch.is_grad_enabled() and (x.requires_grad or flow12.requires_grad):
+        raise RuntimeError("rpeflow_b200.backwarp_2d: forward only; run training through the reference's torch ops")
+    feat = x.contiguous().float()
+    flow = flow12.contiguous().float()
+    B, C, H, W = feat.shape
+    out = torch.empty_like(feat)
+    with torch.cuda.device(feat.device):
+        check(lib.b200_backwarp2d(feat.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, _stream(feat)),
+              "b200_backwarp2d")
     return out
 
 

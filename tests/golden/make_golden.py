@@ -191,8 +191,23 @@ def interpolation():
          xyz2=xyz2, flow12=flow, backwarp=warp)
 
 
+def warp2d():
+    """f3: backwarp_2d (border) and the decode expression leaky_relu(correlation2d(f1, backwarp_2d(f2, flow)), 0.1)."""
+    from torch.nn.functional import leaky_relu
+    gen = torch.Generator().manual_seed(77)
+    f1 = torch.randn(2, 8, 12, 20, generator=gen)
+    f2 = torch.randn(2, 8, 12, 20, generator=gen)
+    flow = 3.0 * torch.randn(2, 2, 12, 20, generator=gen)        # many samples leave the image: the border clamp decides
+    flow[0, :, 0, 0] = torch.tensor([-50.0, -50.0])
+    flow[0, :, 11, 19] = torch.tensor([50.0, 50.0])
+    flow[1, :, 5, 5] = 0.0                                        # exact pixel hit
+    warped = mutils.backwarp_2d(f2, flow, padding_mode='border')
+    cost = leaky_relu(correlation2d(f1, warped, 4), 0.1)
+    save("warp2d", f1=f1, f2=f2, flow=flow, warped=warped, cost=cost)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (corr2d, fps, knn, gathers, projection, corr3d, events, interpolation, pointconv):
+    for fn in (corr2d, fps, knn, gathers, projection, corr3d, events, interpolation, pointconv, warp2d):
         if not only or fn.__name__ in only:
             fn()

@@ -123,6 +123,7 @@ assert pc.PointConvNoSampling(8, 8)(x, torch.rand(1, 8, 50)).shape == (1, 8, 50)
 assert pc.PointConvDownSampling(8, 8)(x, torch.rand(1, 8, 50), x[:, :, :20]).shape == (1, 8, 20)
 assert mu.knn_interpolation(x, torch.rand(1, 5, 50), torch.rand(1, 3, 70)).shape == (1, 5, 70)
 assert core.correlation2d(torch.rand(1, 4, 8, 8), torch.rand(1, 4, 8, 8), 4).shape == (1, 81, 8, 8)
+assert mu.backwarp_2d(torch.rand(1, 4, 8, 8), torch.rand(1, 2, 8, 8), 'border').shape == (1, 4, 8, 8)
 print('SHIMS-OK')
 """
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)

@@ -531,6 +531,46 @@ def test_knn_interpolation_golden_and_levels(golden):
         b200.knn_interpolation(xin, feat, xq, 3)                                              # CPU tensors: no fallback
 
 
+# ------------------------------------------------------------------------------------------------- backwarp_2d + corr2d + leaky (§8f rank 3)
+def test_warp2d_golden(golden):
+    g = golden("warp2d")
+    warped = b200.backwarp_2d(cu(g["f2"]), cu(g["flow"]), "border")
+    np.testing.assert_allclose(warped.cpu().numpy(), g["warped"], rtol=1e-5, atol=1e-5)       # the reference's own output
+    cost = b200.warp_correlate(cu(g["f1"]), cu(g["f2"]), cu(g["flow"]), 4, 0.1)
+    np.testing.assert_allclose(cost.cpu().numpy(), g["cost"], rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        b200.backwarp_2d(cu(g["f2"]), cu(g["flow"]), "zeros")                                  # only the mode RPEFlow uses
+    with pytest.raises(RuntimeError):
+        b200.backwarp_2d(torch.from_numpy(g["f2"]), torch.from_numpy(g["flow"]))               # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 32, 144, 240), (2, 64, 72, 120), (2, 96, 36, 60), (1, 5, 9, 16), (2, 33, 18, 28)])
+def test_warp_correlate_vs_oracle(B, C, H, W):
+    """Level shapes of config 1 (both corr2d tilings) and ragged ones; flows large enough to leave the image."""
+    gen = torch.Generator().manual_seed(H * W + C)
+    f1 = torch.randn(B, C, H, W, generator=gen)
+    f2 = torch.randn(B, C, H, W, generator=gen)
+    flow = 4.0 * torch.randn(B, 2, H, W, generator=gen)
+    warped = b200.backwarp_2d(f2.to(DEV), flow.to(DEV))
+    want_w = spec.backwarp2d_border(f2.numpy(), flow.numpy())
+    np.testing.assert_allclose(warped.cpu().numpy(), want_w, rtol=1e-5, atol=1e-5)
+    ref_w = torch_ref.backwarp_2d(f2, flow, "border")
+    np.testing.assert_allclose(warped.cpu().numpy(), ref_w.numpy(), rtol=1e-5, atol=1e-5)
+    # the fused activation is exactly leaky_relu of the unfused cost volume, on both tilings and on the NHWC fallback
+    plain = b200.correlation2d(f1.to(DEV), warped, 4)
+    leaky = b200.correlation2d_leaky(f1.to(DEV), warped, 4, 0.1)
+    assert torch.equal(leaky, torch.nn.functional.leaky_relu(plain, 0.1))
+    assert torch.equal(b200.correlation2d_leaky(f1.to(DEV), warped, 4, 1.0), plain)
+    # whole expression vs the oracle, chunked (warped map kept L2-sized) and unchunked
+    want = spec.corr2d_fwd(nhwc(f1.numpy()), nhwc(want_w), 4)
+    want = np.where(want > 0, want, np.float32(0.1) * want)
+    for budget in (48 << 20, 1):
+        got = b200.warp_correlate(f1.to(DEV), f2.to(DEV), flow.to(DEV), 4, 0.1, l2_budget_bytes=budget)
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=2e-6)
+    none = b200.warp_correlate(f1.to(DEV), f2.to(DEV), None, 4, 0.1)                           # coarsest level: no warp
+    assert torch.equal(none, b200.correlation2d_leaky(f1.to(DEV), f2.to(DEV), 4, 0.1))
+
+
 # ------------------------------------------------------------------------------------------------- PointConv (§8f rank 1)
 @pytest.mark.parametrize("precision,tol", [(2, 1e-4), (1, 5e-3)])
 @pytest.mark.parametrize("tag", ["down", "nosample"])

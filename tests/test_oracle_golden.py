@@ -144,6 +144,20 @@ def test_knn_interpolation_oracle_matches_reference_fixture(golden):
     assert torch.equal(torch_ref.backwarp_3d(t(g["input_xyz"]), t(g["xyz2"]), t(g["flow12"]), 3), t(g["backwarp"]))
 
 
+def test_warp2d_oracle_matches_reference_fixture(golden):
+    """backwarp_2d (models/utils.py:186-198, border) and RPEFlow_core.py:351+362."""
+    g = golden("warp2d")
+    t = lambda a: torch.from_numpy(a)
+    assert torch.equal(torch_ref.backwarp_2d(t(g["f2"]), t(g["flow"]), "border"), t(g["warped"]))
+    assert torch.equal(torch_ref.warp_correlate(t(g["f1"]), t(g["f2"]), t(g["flow"]), 4, 0.1), t(g["cost"]))
+    got = spec.backwarp2d_border(g["f2"], g["flow"])
+    np.testing.assert_allclose(got, g["warped"], rtol=1e-5, atol=1e-5)
+    nhwc = lambda a: np.ascontiguousarray(np.transpose(a, (0, 2, 3, 1)))
+    cost = spec.corr2d_fwd(nhwc(g["f1"]), nhwc(got), 4)
+    cost = np.where(cost > 0, cost, np.float32(0.1) * cost)
+    np.testing.assert_allclose(cost, g["cost"], rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("tag", ["down", "nosample"])
 def test_pointconv_oracle_matches_reference_fixture(golden, tag):
     """models/pointconv.py:33-61 / :90-122 (fixtures from the unmodified reference modules)."""
