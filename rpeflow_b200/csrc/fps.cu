@@ -145,6 +145,197 @@ fps_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int N, int 
     if (CS > 1) cg::this_cluster().sync();               // no CTA may exit while peers can still write its smem
 }
 
+// ---- pruned variant (one CTA per cloud, N <= 8192) --------------------------------------------------------------------
+// The scan above touches every point in every iteration, and at one cloud per SM that IS the cost: 2.1 G distance
+// updates per 64 clouds, ~72 % of the SM's issue slots.  But an update only changes dist[i] when the new centre is
+// closer to point i than every earlier sample, which after a few hundred samples is true for a few percent of the
+// cloud.  So the points are first sorted along a Morton curve (one bitonic sort in shared memory per cloud), which
+// makes every group of 32 consecutive points — one register "row" of a warp: the i-th point of each lane — a
+// compact bucket with a bounding box and a cached (max distance, lowest index holding it).  Per iteration lane i of
+// a warp tests row i: it evaluates the distance rule on the gap vector from the centre to the row's box,
+//     g = max(fl(lo - c), fl(c - hi), 0) per axis,   d_box = ((gx*gx + gy*gy) + gz*gz)   (same non-fused fp32 ops);
+// fp32 subtraction, multiplication and addition are monotone, so d_box <= the rule's distance of EVERY point in the
+// box, and d_box >= the row's cached max proves that no dist[] of the row changes: the row is skipped, its cache
+// stays valid.  Rows that fail the test are updated exactly as in the full scan and their cache is recomputed with
+// two redux.  The running distances are therefore bit-identical to the full scan's at every iteration, and with the
+// (max distance, lowest original index) argmax so is every output index (tests: vs oracle, vs the full-scan kernel).
+
+__device__ __forceinline__ unsigned fps_orderable(float v) {          // monotone float -> uint map (for redux min/max)
+    const unsigned b = __float_as_uint(v);
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float fps_unorder(unsigned u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+__device__ __forceinline__ unsigned fps_spread5(unsigned v) {         // 5 bits -> every third bit
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
+}
+
+template <int PPT, int FP_T>
+__global__ void __launch_bounds__(FP_T, 1)
+fps_pruned_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int N, int S) {
+    constexpr int NP = PPT * FP_T, NW = FP_T / 32, RS = NW * 32;     // RS: slots between consecutive rows of a thread
+    static_assert(PPT % 4 == 0 && PPT <= 32 && NP <= 8192, "rows are tested by lanes and visited in groups of four");
+    __shared__ unsigned s_key[NP];                       // sort keys, then the original index of every sorted slot
+    __shared__ float s_red[6][NW];
+    __shared__ unsigned s_d[2][NW], s_i[2][NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* P = xyz + (size_t)blockIdx.x * N * 3;
+
+    // bounding box of the cloud (NaNs dropped by fminf/fmaxf)
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = tid; i < N; i += FP_T)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float v = __ldg(P + (size_t)i * 3 + d);
+            mn[d] = fminf(mn[d], v);
+            mx[d] = fmaxf(mx[d], v);
+        }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        mn[d] = fps_unorder(__reduce_min_sync(FULL, fps_orderable(mn[d])));
+        mx[d] = fps_unorder(__reduce_max_sync(FULL, fps_orderable(mx[d])));
+        if (lane == 0) { s_red[d][warp] = mn[d]; s_red[3 + d][warp] = mx[d]; }
+    }
+    __syncthreads();
+    float ext = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { mn[d] = fminf(mn[d], s_red[d][w]); mx[d] = fmaxf(mx[d], s_red[3 + d][w]); }
+        ext = fmaxf(ext, mx[d] - mn[d]);
+    }
+    const float scale = (ext > 0.0f && ext < 3.0e38f) ? 31.99f / ext : 0.0f;     // cubic cells: 32 per longest axis
+    // Morton keys (any grouping is correct; this one makes the rows compact)
+    for (int i = tid; i < NP; i += FP_T) {
+        unsigned key = 0xFFFFFFFFu;                      // padding sorts to the end
+        if (i < N) {
+            unsigned code = 0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int c = (int)((__ldg(P + (size_t)i * 3 + d) - mn[d]) * scale);   // NaN -> 0
+                code |= fps_spread5((unsigned)min(max(c, 0), 31)) << d;
+            }
+            key = (code << 13) | (unsigned)i;
+        }
+        s_key[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= NP; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < NP / 2; t += FP_T) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const unsigned a = s_key[i], b = s_key[l];
+                if ((a > b) == ((i & k) == 0)) { s_key[i] = b; s_key[l] = a; }
+            }
+            __syncthreads();
+        }
+
+    // registers: row i of this thread = sorted slot (i*NW + warp)*32 + lane, i.e. bucket i*NW + warp — neighbouring
+    // buckets (the ones a new centre activates together) belong to different warps, so the visits spread over the CTA
+    float px[PPT], py[PPT], pz[PPT], dist[PPT];
+    unsigned* my_idx = s_key + warp * 32 + lane;         // my_idx[i*RS]: original index of row i's point (0xFFFFFFFF: none)
+    float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f, rmax_d = 0.0f;
+    unsigned rmax_i = 0xFFFFFFFFu;
+    bool rstale = false;                                 // rmax_i is recomputed lazily, only for a row that holds the warp's max
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const unsigned key = my_idx[i * RS];
+        const bool ok = key != 0xFFFFFFFFu;
+        const unsigned oi = ok ? (key & 8191u) : 0xFFFFFFFFu;
+        px[i] = ok ? __ldg(P + (size_t)oi * 3 + 0) : 0.0f;
+        py[i] = ok ? __ldg(P + (size_t)oi * 3 + 1) : 0.0f;
+        pz[i] = ok ? __ldg(P + (size_t)oi * 3 + 2) : 0.0f;
+        dist[i] = ok ? 1e10f : 0.0f;
+        // row box over the lanes that hold a point; an empty row gets (+big, -big): its gap is huge, it is never visited
+        const float bx0 = fps_unorder(__reduce_min_sync(FULL, fps_orderable(ok ? px[i] : 3.0e38f)));
+        const float by0 = fps_unorder(__reduce_min_sync(FULL, fps_orderable(ok ? py[i] : 3.0e38f)));
+        const float bz0 = fps_unorder(__reduce_min_sync(FULL, fps_orderable(ok ? pz[i] : 3.0e38f)));
+        const float bx1 = fps_unorder(__reduce_max_sync(FULL, fps_orderable(ok ? px[i] : -3.0e38f)));
+        const float by1 = fps_unorder(__reduce_max_sync(FULL, fps_orderable(ok ? py[i] : -3.0e38f)));
+        const float bz1 = fps_unorder(__reduce_max_sync(FULL, fps_orderable(ok ? pz[i] : -3.0e38f)));
+        const unsigned any = __reduce_min_sync(FULL, oi);
+        if (lane == i) {
+            lox = bx0; loy = by0; loz = bz0; hix = bx1; hiy = by1; hiz = bz1;
+            rmax_d = any != 0xFFFFFFFFu ? 1e10f : 0.0f;
+            rmax_i = any;
+        }
+    }
+    __syncthreads();                                     // every key has been read before the slots are rewritten
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const unsigned key = my_idx[i * RS];
+        my_idx[i * RS] = key != 0xFFFFFFFFu ? (key & 8191u) : 0xFFFFFFFFu;
+    }
+    __syncwarp();                                        // a thread only ever reads its own slots again
+
+    unsigned cur = 0;
+    float cx = __ldg(P + 0), cy = __ldg(P + 1), cz = __ldg(P + 2);
+    int64_t* o = out + (size_t)blockIdx.x * S;
+    for (int s = 0; s < S; ++s) {
+        if (tid == 0) o[s] = (int64_t)cur;
+        if (s == S - 1) break;
+
+        // which rows can change?  lane i answers for row i
+        const float gx = fmaxf(fmaxf(__fsub_rn(lox, cx), __fsub_rn(cx, hix)), 0.0f);
+        const float gy = fmaxf(fmaxf(__fsub_rn(loy, cy), __fsub_rn(cy, hiy)), 0.0f);
+        const float gz = fmaxf(fmaxf(__fsub_rn(loz, cz), __fsub_rn(cz, hiz)), 0.0f);
+        const float dbox = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+        const unsigned mask = __ballot_sync(FULL, lane < PPT && !(dbox >= rmax_d));
+#pragma unroll
+        for (int g4 = 0; g4 < PPT; g4 += 4) {
+            if (((mask >> g4) & 0xFu) == 0u) continue;   // warp-uniform
+#pragma unroll
+            for (int i = g4; i < g4 + 4; ++i) {
+                if (!((mask >> i) & 1u)) continue;       // warp-uniform
+                const float d = sqdist3_rule(px[i], py[i], pz[i], cx, cy, cz);
+                dist[i] = fminf(dist[i], d);
+                const unsigned m = __reduce_max_sync(FULL, __float_as_uint(dist[i]));   // >= +0: bit order = value order
+                if (lane == i) { rmax_d = __uint_as_float(m); rstale = true; }
+            }
+        }
+        const unsigned vd = lane < PPT ? __float_as_uint(rmax_d) : 0u;
+        const unsigned wmax = __reduce_max_sync(FULL, vd);
+        const unsigned need = __ballot_sync(FULL, lane < PPT && vd == wmax && rstale);
+        if (need) {                                      // usually one row: lowest original index among its maxima
+#pragma unroll
+            for (int g4 = 0; g4 < PPT; g4 += 4) {
+                if (((need >> g4) & 0xFu) == 0u) continue;
+#pragma unroll
+                for (int i = g4; i < g4 + 4; ++i) {
+                    if (!((need >> i) & 1u)) continue;
+                    const unsigned mi = __reduce_min_sync(FULL, __float_as_uint(dist[i]) == wmax ? my_idx[i * RS] : 0xFFFFFFFFu);
+                    if (lane == i) { rmax_i = mi; rstale = false; }
+                }
+            }
+        }
+        const unsigned widx = __reduce_min_sync(FULL, (lane < PPT && vd == wmax) ? rmax_i : 0xFFFFFFFFu);
+        const int par = s & 1;
+        if (lane == 0) { s_d[par][warp] = wmax; s_i[par][warp] = widx; }
+        __syncthreads();
+        const unsigned qd = lane < NW ? s_d[par][lane] : 0u;
+        const unsigned qi = lane < NW ? s_i[par][lane] : 0xFFFFFFFFu;
+        const unsigned gmax = __reduce_max_sync(FULL, qd);
+        cur = __reduce_min_sync(FULL, qd == gmax ? qi : 0xFFFFFFFFu);
+        cx = __ldg(P + (size_t)cur * 3 + 0);
+        cy = __ldg(P + (size_t)cur * 3 + 1);
+        cz = __ldg(P + (size_t)cur * 3 + 2);
+    }
+}
+
+template <int PPT, int FP_T>
+static cudaError_t launch_fps_pruned(const float* xyz, int64_t* idx, int B, int N, int S, cudaStream_t st) {
+    fps_pruned_kernel<PPT, FP_T><<<B, FP_T, 0, st>>>(xyz, idx, N, S);
+    return cudaGetLastError();
+}
+
+static cudaError_t dispatch_pruned(const float* xyz, int64_t* idx, int B, int N, int S, cudaStream_t st) {
+    if (N <= 1024) return launch_fps_pruned<4, 256>(xyz, idx, B, N, S, st);
+    if (N <= 2048) return launch_fps_pruned<4, 512>(xyz, idx, B, N, S, st);
+    if (N <= 4096) return launch_fps_pruned<8, 512>(xyz, idx, B, N, S, st);
+    return launch_fps_pruned<16, 512>(xyz, idx, B, N, S, st);
+}
+
 template <int PPT, int T, int CS>
 static cudaError_t launch_fps(const float* xyz, int64_t* idx, int B, int N, int S, cudaStream_t st) {
     auto kern = fps_kernel<PPT, T, CS>;
@@ -201,6 +392,12 @@ extern "C" int b200_fps(const float* xyz, int64_t* idx, int B, int N, int n_samp
     }
     cudaStream_t st = as_stream(stream);
     cudaError_t e;
+    const char* full = getenv("B200_FPS_FULL_SCAN");                 // measurement knob: "1" = the unpruned kernel
+    if (cs == 1 && !(full && full[0] == '1')) {
+        e = dispatch_pruned(xyz, idx, B, N, n_samples, st);
+        if (e != cudaSuccess) return cuda_fail(e, "b200_fps");
+        return B200_OK;
+    }
     switch (cs) {
         case 1: e = dispatch_ppt<1>(xyz, idx, B, N, n_samples, st); break;
         case 2: e = dispatch_ppt<2>(xyz, idx, B, N, n_samples, st); break;

@@ -217,6 +217,43 @@ def test_fps_sizes_exact(B, N, S):
     np.testing.assert_array_equal(got, spec.fps(xyz, S))
 
 
+def _fps_adversarial_clouds():
+    rng = np.random.default_rng(5)
+    N = 3000
+    dup = rng.random((N, 3), dtype=np.float32); dup[1000:2000] = dup[:1000]            # sampled with replacement
+    clus = (rng.random((N, 3), dtype=np.float32) * 0.01 + rng.integers(0, 3, (N, 1)).astype(np.float32)); clus[7] = 50.0
+    plane = rng.random((N, 3), dtype=np.float32); plane[:, 2] = 0.25
+    line = np.zeros((N, 3), np.float32); line[:, 0] = rng.random(N, dtype=np.float32)
+    same = np.full((N, 3), 1.5, np.float32)
+    lattice = np.stack(np.meshgrid(*[np.arange(15, dtype=np.float32)] * 3, indexing="ij"), -1).reshape(-1, 3)[:N]   # exact ties
+    ft3d = rng.random((N, 3), dtype=np.float32) * np.array([30, 17, 90], np.float32) + np.array([-15, -8, 22], np.float32)
+    big = (rng.random((N, 3), dtype=np.float32) - 0.5) * 2e4
+    return {"dup": dup, "clusters+outlier": clus, "plane": plane, "line": line, "identical": same,
+            "lattice": np.ascontiguousarray(lattice), "ft3d": ft3d, "large": big}
+
+
+def test_fps_pruned_scan_exact(monkeypatch):
+    """The bounding-box pruned kernel (default for N <= 8192) returns the full scan's indices on every cloud: vs the
+    oracle and vs the unpruned kernel (B200_FPS_FULL_SCAN=1)."""
+    clouds = _fps_adversarial_clouds()
+    xyz = np.stack(list(clouds.values()))
+    S = 1500
+    want = spec.fps(xyz, S)
+    got = b200.ops._furthest_point_sampling_cuda(cu(xyz), S).cpu().numpy()
+    for i, name in enumerate(clouds):
+        np.testing.assert_array_equal(got[i], want[i], err_msg=name)
+    monkeypatch.setenv("B200_FPS_FULL_SCAN", "1")
+    full = b200.ops._furthest_point_sampling_cuda(cu(xyz), S).cpu().numpy()
+    np.testing.assert_array_equal(full, want)
+    monkeypatch.delenv("B200_FPS_FULL_SCAN")
+    # full-size cloud (config 1), both kernels agree on all 4096 picks
+    g = torch.Generator().manual_seed(12)
+    big = (torch.rand(6, 8192, 3, generator=g) * torch.tensor([30.0, 17.0, 90.0])).to(DEV)
+    a = b200.ops._furthest_point_sampling_cuda(big, 4096)
+    monkeypatch.setenv("B200_FPS_FULL_SCAN", "1")
+    assert torch.equal(a, b200.ops._furthest_point_sampling_cuda(big, 4096))
+
+
 def test_fps_forced_cluster(monkeypatch):
     rng = np.random.default_rng(9)
     xyz = rng.random((3, 8192, 3), dtype=np.float32)
