@@ -333,6 +333,7 @@ static cudaError_t dispatch_pruned(const float* xyz, int64_t* idx, int B, int N,
     if (N <= 1024) return launch_fps_pruned<4, 256>(xyz, idx, B, N, S, st);
     if (N <= 2048) return launch_fps_pruned<4, 512>(xyz, idx, B, N, S, st);
     if (N <= 4096) return launch_fps_pruned<8, 512>(xyz, idx, B, N, S, st);
+    if (const char* t = getenv("B200_FPS_T")) { if (t[0] == '2') return launch_fps_pruned<32, 256>(xyz, idx, B, N, S, st); if (t[0] == '1') return launch_fps_pruned<8, 1024>(xyz, idx, B, N, S, st); }
     return launch_fps_pruned<16, 512>(xyz, idx, B, N, S, st);
 }
 

@@ -337,7 +337,18 @@ knn_grid_query_kernel(const float4* __restrict__ sorted_pts, const int* __restri
             for (int y = y0; y <= y1; ++y) {
                 const int rowbase = (z * Gy + y) * Gx;
                 const int e = __ldg(cs + rowbase + x1 + 1);
-                for (int c = __ldg(cs + rowbase + x0); c < e; ++c) {      // cells x0..x1 of a row are contiguous
+                int c = __ldg(cs + rowbase + x0);                          // cells x0..x1 of a row are contiguous
+                for (; c + KG_STEP <= e; c += KG_STEP) {                   // KG_STEP loads in flight per thread
+                    float4 pt[KG_STEP];
+#pragma unroll
+                    for (int j = 0; j < KG_STEP; ++j) pt[j] = __ldg(sorted_pts + c + j);
+#pragma unroll
+                    for (int j = 0; j < KG_STEP; ++j) {
+                        const u64 key = kg_key<D>(q, pt[j]);
+                        if (key < L[KMAX - 1]) kg_insert<KMAX>(L, key);
+                    }
+                }
+                for (; c < e; ++c) {
                     const u64 key = kg_key<D>(q, __ldg(sorted_pts + c));
                     if (key < L[KMAX - 1]) kg_insert<KMAX>(L, key);
                 }
