@@ -77,6 +77,14 @@ B200_API int b200_corr2d_fwd_nchw_leaky(const float* in1_nchw, const float* in2_
 B200_API int b200_backwarp2d(const float* x_nchw, const float* flow, float* out_nchw,
                     int B, int C, int H, int W, b200_stream_t stream);
 
+/* f4  convex_upsample (models/utils.py:201-214; caller RPEFlow_core.py:424 with scale_factor 4): RAFT's convex upsampling.
+ *   flow : [B,2,H,W];  mask : [B,9*s*s,H,W] (logits; channel = (k*s + i)*s + j, k = 3x3 tap)  ->  out : [B,2,s*H,s*W]
+ *   out[b,c,y*s+i,x*s+j] = sum_k softmax_k(mask[b,:,y,x])[k,i,j] * s * flow[b,c,y+k/3-1,x+k%3-1]   (zeros outside)
+ * s in {2,4,8}; out 16-byte aligned.
+ */
+B200_API int b200_convex_upsample(const float* flow, const float* mask, float* out,
+                         int B, int H, int W, int scale, b200_stream_t stream);
+
 /* a2  backward of a1.
  * Replaces: correlation.cpp:24-35 (correlation_backward_cuda) + correlation_backward_kernel.cu:4-89;
  *           binding `_correlation_backward_cuda` (correlation.cpp:40), called from wrapper.py:31.

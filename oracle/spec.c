@@ -306,6 +306,35 @@ ORC_API void orc_backwarp2d_border(const float* x, const float* flow, float* out
                 }
 }
 
+/* f4 convex_upsample — models/utils.py:201-214: softmax over the 9 taps, F.unfold(flow*s, 3x3, padding=1), weighted sum,
+ * permute to [B,2,H*s,W*s].  mask channel = (k*s + i)*s + j. */
+ORC_API void orc_convex_upsample(const float* flow, const float* mask, float* out, int B, int H, int W, int s) {
+    const size_t HW = (size_t)H * W;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x)
+                for (int i = 0; i < s; ++i)
+                    for (int j = 0; j < s; ++j) {
+                        float v[9], mx = -INFINITY, sum = 0.0f;
+                        for (int k = 0; k < 9; ++k) {
+                            v[k] = mask[((size_t)b * 9 * s * s + (size_t)(k * s + i) * s + j) * HW + (size_t)y * W + x];
+                            if (v[k] > mx) mx = v[k];
+                        }
+                        for (int k = 0; k < 9; ++k) { v[k] = expf(v[k] - mx); sum += v[k]; }
+                        for (int c = 0; c < 2; ++c) {
+                            float acc = 0.0f;
+                            for (int k = 0; k < 9; ++k) {
+                                int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+                                float f = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                                              ? flow[((size_t)b * 2 + c) * HW + (size_t)yy * W + xx] * (float)s : 0.0f;
+                                acc += (v[k] / sum) * f;
+                            }
+                            out[(((size_t)b * 2 + c) * H * s + (size_t)y * s + i) * W * s + (size_t)x * s + j] = acc;
+                        }
+                    }
+}
+
 /* a8 project_feat_with_nn_corr — models/utils.py:297-317 with nn_indices given. */
 ORC_API void orc_project_nn_corr(const float* xy, const float* feat2d, const float* feat3d,
                                  const int64_t* nn, float* out,

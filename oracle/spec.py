@@ -120,6 +120,15 @@ def backwarp2d_border(x, flow):
     return out
 
 
+def convex_upsample(flow, mask, s):
+    """flow [B,2,H,W], mask [B,9*s*s,H,W] -> [B,2,s*H,s*W] (models/utils.py:201-214)."""
+    flow, mask = _f32(flow), _f32(mask)
+    B, _, H, W = flow.shape
+    out = np.empty((B, 2, H * s, W * s), np.float32)
+    lib().orc_convex_upsample(_p(flow), _p(mask), _p(out), B, H, W, int(s))
+    return out
+
+
 def project_nn_corr(xy, feat2d, feat3d, nn):
     xy, feat2d, feat3d, nn = _f32(xy), _f32(feat2d), _f32(feat3d), _i64(nn)
     B, C2, H, W = feat2d.shape

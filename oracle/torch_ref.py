@@ -222,6 +222,15 @@ def warp_correlate(feat1, feat2, flow, md=4, negative_slope=0.1):
     return F.leaky_relu(correlation2d(feat1, warped, md), negative_slope)
 
 
+# ------------------------------------------------------------------ f4  models/utils.py:201-214
+def convex_upsample(flow, mask, scale_factor=8):
+    nb, _, h, w = flow.shape
+    mask = torch.softmax(mask.view(nb, 1, 9, scale_factor, scale_factor, h, w), dim=2)
+    up = F.unfold(flow * scale_factor, [3, 3], padding=1).view(nb, 2, 9, 1, 1, h, w)
+    up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(nb, 2, h * scale_factor, w * scale_factor)
+
+
 def pointconv(xyz, features, sampled_xyz, wts, k=16, knn=None):
     """models/pointconv.py:33-61 (and :90-122 with sampled_xyz = xyz).  wts: Wa [8,3], ba, Wb [16,8], bb, L, bias."""
     lrelu = lambda t: F.leaky_relu(t, 0.1)

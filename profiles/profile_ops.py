@@ -78,7 +78,20 @@ def once():
     b200.project_feat_with_nn_corr(xy_cf, feat2d, feat3d, nn[..., 0])
     b200.batch_indexing_channel_first(feat3d, knn11)
     events.events_to_voxel_device(ev, 10, 540, 960, True, check_range=False)
+    # rows widened this round: PointConv 8192 -> 4096 (C=32 -> 64), backwarp_2d + fused leaky correlation
+    b200.pointconv_forward(xyz_big_cf, feat_big, xyz_cf, knn_pyr, pcw)
+    flow = 2.0 * torch.randn(B, 2, H, W, device=dev)
+    b200.correlation2d_leaky(feat2d, b200.backwarp_2d(feat2d_b, flow), 4, 0.1)
 
+
+if ONLY == "":
+    from rpeflow_b200 import pointconv as _pc
+    import importlib
+    xyz_big_cf = xyz_big.transpose(1, 2).contiguous()
+    feat_big = torch.randn(B, C, 8192, generator=g).to(dev)
+    knn_pyr = ops._k_nearest_neighbor_cuda(xyz_big, xyz, 16)
+    torch.manual_seed(0)
+    pcw = {n: v.to(dev) for n, v in _pc.pack_pointconv_weights(_pc.PointConvDownSampling(C, 64)).items()}
 
 for _ in range(2):
     once()

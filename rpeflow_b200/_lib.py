@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200_corr2d_fwd_nchw": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "b200_corr2d_fwd_nchw_leaky": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, ctypes.c_float, c_p]),
     "b200_backwarp2d": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "b200_convex_upsample": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "b200_corr2d_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "b200_fps": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "b200_knn": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),

@@ -201,6 +201,67 @@ backwarp2d_border_kernel(const float* __restrict__ x, const float* __restrict__ 
     }
 }
 
+// f4: convex_upsample (models/utils.py:201-214; caller RPEFlow_core.py:424, scale 4): RAFT's learned upsampling.
+//   out[b,c,y*s+i,x*s+j] = sum_k softmax_k(mask[b,(k*s+i)*s+j,y,x]) * (s * flow[b,c,y+ky-1,x+kx-1]),  k = ky*3+kx, zero padding.
+// Thread = (low-res pixel, sub-row i): reads its 9*s mask values plane by plane (coalesced over x), the 3x3 flow
+// patch once, and writes the s output pixels of its sub-row for both flow channels as contiguous runs
+// (16 bytes per thread for s = 4, adjacent threads adjacent in memory).  HBM-bound: the mask is 9*s*s planes.
+template <int S>
+__global__ void __launch_bounds__(256)
+convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, float* __restrict__ out, int H, int W) {
+    const int b = blockIdx.z, i = blockIdx.y;
+    const int HW = H * W;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= HW) return;
+    const int y = p / W, x = p - y * W;
+    float f[2][9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;                    // F.unfold(padding=1): zeros outside
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            f[c][k] = in ? __fmul_rn(__ldg(flow + ((size_t)b * 2 + c) * HW + yy * W + xx), (float)S) : 0.0f;
+    }
+    const float* m = mask + (size_t)b * 9 * S * S * HW + p;
+    float o[2][S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        float v[9], mx = -3.402823466e38f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            v[k] = __ldg(m + (size_t)((k * S + i) * S + j) * HW);
+            mx = fmaxf(mx, v[k]);
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            v[k] = expf(v[k] - mx);                                                  // torch.softmax: exp(x - max) / sum
+            sum += v[k];
+        }
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float w = __fdiv_rn(v[k], sum);
+            a0 += w * f[0][k];
+            a1 += w * f[1][k];
+        }
+        o[0][j] = a0; o[1][j] = a1;
+    }
+    const size_t OW = (size_t)W * S, OHW = (size_t)H * S * OW;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        float* dst = out + ((size_t)b * 2 + c) * OHW + (size_t)(y * S + i) * OW + (size_t)x * S;
+        if (S % 4 == 0) {
+#pragma unroll
+            for (int j = 0; j < S; j += 4) __stcs(reinterpret_cast<float4*>(dst + j), make_float4(o[c][j], o[c][j + 1], o[c][j + 2], o[c][j + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j) dst[j] = o[c][j];
+        }
+    }
+}
+
 // a8, pass 1: S[b,n,c] = bilinear(feat2d[b,c], xy[b,:,n])  (point-major scratch).  Block = 16 points; compute: a warp
 // owns 4 of every 32 channels, lanes = 16 points x 2 tap sides (see half_taps); write: lane = channel (contiguous in S).
 __global__ void __launch_bounds__(256)
@@ -411,6 +472,24 @@ extern "C" int b200_backwarp2d(const float* x, const float* flow, float* out, in
     dim3 grid(ceil_div(HW, 128), csplit, B);
     backwarp2d_border_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, flow, out, C, H, W);
     B200_LAUNCH_CHECK("b200_backwarp2d");
+    return B200_OK;
+}
+
+extern "C" int b200_convex_upsample(const float* flow, const float* mask, float* out, int B, int H, int W, int scale,
+                                    b200_stream_t stream) {
+    using namespace b200;
+    B200_REQUIRE(flow && mask && out, "b200_convex_upsample: null pointer");
+    B200_REQUIRE(B >= 0 && H >= 1 && W >= 1, "b200_convex_upsample: bad sizes");
+    B200_REQUIRE(scale == 2 || scale == 4 || scale == 8, "b200_convex_upsample: scale_factor must be 2, 4 or 8 (got %d)", scale);
+    B200_REQUIRE((int64_t)H * W * scale * scale < (1ll << 31) && B <= 65535, "b200_convex_upsample: plane or batch too large");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "b200_convex_upsample: out must be 16-byte aligned");
+    if (B == 0) return B200_OK;
+    dim3 grid(ceil_div((int64_t)H * W, 256), scale, B);
+    cudaStream_t st = as_stream(stream);
+    if (scale == 2) convex_upsample_kernel<2><<<grid, 256, 0, st>>>(flow, mask, out, H, W);
+    else if (scale == 4) convex_upsample_kernel<4><<<grid, 256, 0, st>>>(flow, mask, out, H, W);
+    else convex_upsample_kernel<8><<<grid, 256, 0, st>>>(flow, mask, out, H, W);
+    B200_LAUNCH_CHECK("b200_convex_upsample");
     return B200_OK;
 }
 

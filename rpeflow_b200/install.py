@@ -127,6 +127,13 @@ def patch_python_ops(patch_events=True):
     replaced["knn_interpolation"] = knn_interpolation
     replaced["backwarp_3d"] = backwarp_3d
     replaced["backwarp_2d"] = backwarp_2d
+    ref_convex = mutils.convex_upsample
+
+    def convex_upsample(flow, mask, scale_factor=8):
+        if not flow.is_cuda or scale_factor not in (2, 4, 8) or (torch.is_grad_enabled() and (flow.requires_grad or mask.requires_grad)):
+            return ref_convex(flow, mask, scale_factor)
+        return projection.convex_upsample(flow, mask, scale_factor)
+    replaced["convex_upsample"] = convex_upsample
     for modname in ("models.utils", "models.RPEFlow_core", "models.pwc2d_core", "models.pwc3d_core", "models.pointconv",
                     "models.losses3d", "models.RPEFlow", "models.csrc", "models.csrc.wrapper"):
         try:

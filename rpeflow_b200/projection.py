@@ -10,7 +10,7 @@ import torch
 
 from ._lib import check, lib
 
-__all__ = ["batch_indexing_channel_first", "batch_indexing_channel_last", "grid_sample_wrapper", "backwarp_2d",
+__all__ = ["batch_indexing_channel_first", "batch_indexing_channel_last", "grid_sample_wrapper", "backwarp_2d", "convex_upsample",
            "project_feat_with_nn_corr", "knn_interpolation", "backwarp_3d"]
 
 
@@ -98,6 +98,25 @@ def backwarp_2d(x, flow12, padding_mode="border"):
     with torch.cuda.device(feat.device):
         check(lib.b200_backwarp2d(feat.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, _stream(feat)),
               "b200_backwarp2d")
+    return out
+
+
+def convex_upsample(flow, mask, scale_factor=8):
+    """flow [B,2,H,W], mask [B,9*s*s,H,W] -> [B,2,s*H,s*W]: convex combination of the 3x3 neighbourhood with softmax
+    weights (models/utils.py:201-214).  Forward only (the model trains through the reference's torch ops)."""
+    if not (flow.is_cuda and mask.is_cuda):
+        raise RuntimeError("rpeflow_b200.convex_upsample: CUDA tensors required — no CPU/torch fallback")
+    if torch.is_grad_enabled() and (flow.requires_grad or mask.requires_grad):
+        raise RuntimeError("rpeflow_b200.convex_upsample: forward only; run training through the reference's torch ops")
+    s = int(scale_factor)
+    B, C, H, W = flow.shape
+    if C != 2 or s not in (2, 4, 8) or tuple(mask.shape) != (B, 9 * s * s, H, W):
+        raise RuntimeError("rpeflow_b200.convex_upsample: needs flow [B,2,H,W], mask [B,9*s*s,H,W], s in {2,4,8}")
+    f, m = flow.contiguous().float(), mask.contiguous().float()
+    out = torch.empty((B, 2, H * s, W * s), dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        check(lib.b200_convex_upsample(f.data_ptr(), m.data_ptr(), out.data_ptr(), B, H, W, s, _stream(f)),
+              "b200_convex_upsample")
     return out
 
 

@@ -206,8 +206,17 @@ def warp2d():
     save("warp2d", f1=f1, f2=f2, flow=flow, warped=warped, cost=cost)
 
 
+def upsample():
+    """f4: convex_upsample at the model's scale (4, RPEFlow_core.py:424) and at the default 8."""
+    gen = torch.Generator().manual_seed(88)
+    for s, (h, w) in ((4, (9, 14)), (8, (5, 6))):
+        flow = 5.0 * torch.randn(2, 2, h, w, generator=gen)
+        mask = 3.0 * torch.randn(2, 9 * s * s, h, w, generator=gen)
+        save("convex_upsample_s%d" % s, flow=flow, mask=mask, s=s, out=mutils.convex_upsample(flow, mask, scale_factor=s))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (corr2d, fps, knn, gathers, projection, corr3d, events, interpolation, pointconv, warp2d):
+    for fn in (corr2d, fps, knn, gathers, projection, corr3d, events, interpolation, pointconv, warp2d, upsample):
         if not only or fn.__name__ in only:
             fn()

@@ -124,6 +124,7 @@ assert pc.PointConvDownSampling(8, 8)(x, torch.rand(1, 8, 50), x[:, :, :20]).sha
 assert mu.knn_interpolation(x, torch.rand(1, 5, 50), torch.rand(1, 3, 70)).shape == (1, 5, 70)
 assert core.correlation2d(torch.rand(1, 4, 8, 8), torch.rand(1, 4, 8, 8), 4).shape == (1, 81, 8, 8)
 assert mu.backwarp_2d(torch.rand(1, 4, 8, 8), torch.rand(1, 2, 8, 8), 'border').shape == (1, 4, 8, 8)
+assert mu.convex_upsample(torch.rand(1, 2, 4, 4), torch.rand(1, 144, 4, 4), 4).shape == (1, 2, 16, 16)
 print('SHIMS-OK')
 """
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)

@@ -608,6 +608,32 @@ def test_warp_correlate_vs_oracle(B, C, H, W):
     assert torch.equal(none, b200.correlation2d_leaky(f1.to(DEV), f2.to(DEV), 4, 0.1))
 
 
+# ------------------------------------------------------------------------------------------------- convex_upsample (§8f rank 4)
+@pytest.mark.parametrize("s", [4, 8])
+def test_convex_upsample_golden(golden, s):
+    g = golden("convex_upsample_s%d" % s)
+    got = b200.convex_upsample(cu(g["flow"]), cu(g["mask"]), s)
+    np.testing.assert_allclose(got.cpu().numpy(), g["out"], rtol=1e-5, atol=1e-5)             # the reference's own output
+
+
+@pytest.mark.parametrize("B,H,W,s", [(2, 144, 240, 4), (1, 120, 160, 4), (2, 17, 23, 8), (3, 10, 7, 2)])
+def test_convex_upsample_vs_oracle(B, H, W, s):
+    gen = torch.Generator().manual_seed(H + W + s)
+    flow = 4.0 * torch.randn(B, 2, H, W, generator=gen)
+    mask = 2.0 * torch.randn(B, 9 * s * s, H, W, generator=gen)
+    got = b200.convex_upsample(flow.to(DEV), mask.to(DEV), s).cpu().numpy()
+    np.testing.assert_allclose(got, spec.convex_upsample(flow.numpy(), mask.numpy(), s), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(got, torch_ref.convex_upsample(flow, mask, s).numpy(), rtol=1e-5, atol=1e-5)
+    # a one-hot mask copies the chosen neighbour (times s): exact property, size independent
+    hot = torch.full((B, 9, s * s, H, W), -1e4)
+    hot[:, 4] = 1e4                                                                          # centre tap
+    got = b200.convex_upsample(flow.to(DEV), hot.reshape(B, 9 * s * s, H, W).to(DEV), s)
+    want = (flow * s).repeat_interleave(s, dim=2).repeat_interleave(s, dim=3)
+    assert torch.equal(got.cpu(), want)
+    with pytest.raises(RuntimeError):
+        b200.convex_upsample(flow, mask, s)                                                  # CPU tensors: no fallback
+
+
 # ------------------------------------------------------------------------------------------------- PointConv (§8f rank 1)
 @pytest.mark.parametrize("precision,tol", [(2, 1e-4), (1, 5e-3)])
 @pytest.mark.parametrize("tag", ["down", "nosample"])

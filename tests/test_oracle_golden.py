@@ -158,6 +158,15 @@ def test_warp2d_oracle_matches_reference_fixture(golden):
     np.testing.assert_allclose(cost, g["cost"], rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("s", [4, 8])
+def test_convex_upsample_oracle_matches_reference_fixture(golden, s):
+    """convex_upsample (models/utils.py:201-214)."""
+    g = golden("convex_upsample_s%d" % s)
+    t = lambda a: torch.from_numpy(a)
+    assert torch.equal(torch_ref.convex_upsample(t(g["flow"]), t(g["mask"]), s), t(g["out"]))
+    np.testing.assert_allclose(spec.convex_upsample(g["flow"], g["mask"], s), g["out"], rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("tag", ["down", "nosample"])
 def test_pointconv_oracle_matches_reference_fixture(golden, tag):
     """models/pointconv.py:33-61 / :90-122 (fixtures from the unmodified reference modules)."""
