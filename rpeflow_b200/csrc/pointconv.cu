@@ -168,6 +168,16 @@ pointconv_tc_kernel(const float* __restrict__ xyz, const float* __restrict__ sam
             f[kk][4] = v1.x; f[kk][5] = v1.y; f[kk][6] = v1.z; f[kk][7] = v1.w;
         }
         for (int w = 0; w < PC_NW; ++w, ++kbi) {
+            // the B tile's global loads (Lp[o][w*Cp + cb*32 .. +32), L2-resident) go out first: their latency hides under
+            // the 128 FMAs of the A rows and the wait for the previous block's MMAs
+            constexpr int NBV = 256 * 8 / PC_THREADS;          // float4 per thread at out_channels = 256
+            float4 bv[NBV];
+#pragma unroll
+            for (int n = 0; n < NBV; ++n) {
+                const int e = tid + n * PC_THREADS;
+                if (e < Npad * 8)
+                    bv[n] = __ldg(reinterpret_cast<const float4*>(Lp + (size_t)(e >> 3) * lp_row + (size_t)w * Cp + cb * PC_KB + 4 * (e & 7)));
+            }
             float acc[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
@@ -194,9 +204,12 @@ pointconv_tc_kernel(const float* __restrict__ xyz, const float* __restrict__ sam
                     *reinterpret_cast<float4*>(g + Ls.a_hi + off) = v;
                 }
             }
-            for (int e = tid; e < Npad * 8; e += PC_THREADS) {     // B tile: Lp[o][w*Cp + cb*32 .. +32)
+#pragma unroll
+            for (int n = 0; n < NBV; ++n) {                        // B tile into its swizzled rows
+                const int e = tid + n * PC_THREADS;
+                if (e >= Npad * 8) break;
                 const int o = e >> 3, qq = e & 7;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(Lp + (size_t)o * lp_row + (size_t)w * Cp + cb * PC_KB + 4 * qq));
+                const float4 v = bv[n];
                 const uint32_t off = (uint32_t)o * 128u + (uint32_t)((qq ^ (o & 7)) << 4);
                 if (SPLIT) {
                     const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
