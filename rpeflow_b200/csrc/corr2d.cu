@@ -13,6 +13,8 @@
 //     warp hit 8 different 16-byte bank groups (conflict-free LDS.128).
 //   * every in2 value loaded is used by up to 6 pixels x 2 packed lanes; every in1 value by 9 shifts.
 //   * stores: each thread writes 6 consecutive floats per displacement channel, the 4 strips of a row are contiguous.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -252,6 +254,11 @@ corr2d_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ part
     }
 }
 
+bool corr2d_bwd_tiled_eligible(const float* gout, const float* in1, const float* in2, const float* g1, const float* g2,
+                               int B, int C, int H, int W, int md);                       // corr2d_bwd_tiled.cu
+cudaError_t corr2d_bwd_tiled(const float* gout, const float* in1, const float* in2, float* g1, float* g2, int B, int C, int H,
+                             int W, cudaStream_t st);
+
 template <int MD>
 static cudaError_t launch_corr2d_bwd(const float* gout, const float* in1, const float* in2, float* g1, float* g2,
                                      int B, int C, int H, int W, cudaStream_t st) {
@@ -296,6 +303,12 @@ extern "C" int b200_corr2d_bwd(const float* gout, const float* in1, const float*
     B200_REQUIRE(H <= 65535 && B <= 65535, "b200_corr2d_bwd: H or B exceeds the grid limit");
     if (B == 0) return B200_OK;
     cudaError_t e;
+    const char* old_kernel = getenv("B200_CORR2D_BWD_SIMPLE");          // measurement knob: "1" = the first, untiled kernel
+    if (!(old_kernel && old_kernel[0] == '1') && corr2d_bwd_tiled_eligible(gout, in1, in2, gin1, gin2, B, C, H, W, md)) {
+        e = corr2d_bwd_tiled(gout, in1, in2, gin1, gin2, B, C, H, W, as_stream(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "b200_corr2d_bwd(tiled)");
+        return B200_OK;
+    }
     switch (md) {
         case 1: e = launch_corr2d_bwd<1>(gout, in1, in2, gin1, gin2, B, C, H, W, as_stream(stream)); break;
         case 2: e = launch_corr2d_bwd<2>(gout, in1, in2, gin1, gin2, B, C, H, W, as_stream(stream)); break;

@@ -82,14 +82,22 @@ pointwise_linear_kernel(const float* __restrict__ X, const float* __restrict__ W
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
         }
     }
+    const int ob = o0 + tx * 4;
+    float bv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bv[j] = (bias && ob + j < Cout) ? __ldg(bias + ob + j) : 0.0f;
+    const bool vec = (Cout & 3) == 0 && ob + 3 < Cout;               // rows of out are 16-byte aligned when Cout % 4 == 0
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int n = n0 + ty * 4 + i;
         if (n >= N) continue;
+        float* o = out + ((size_t)b * N + n) * Cout + ob;
+        if (vec) {
+            *reinterpret_cast<float4*>(o) = make_float4(acc[i][0] + bv[0], acc[i][1] + bv[1], acc[i][2] + bv[2], acc[i][3] + bv[3]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int o = o0 + tx * 4 + j;
-            if (o < Cout) out[((size_t)b * N + n) * Cout + o] = acc[i][j] + (bias ? __ldg(bias + o) : 0.0f);
+            for (int j = 0; j < 4; ++j)
+                if (ob + j < Cout) o[j] = acc[i][j] + bv[j];
         }
     }
 }

@@ -317,6 +317,25 @@ def test_corr2d_pyramid_levels_vs_oracle(C, H, W):
     assert np.mean(np.abs(got - want)) < 1e-6             # correlation_test.cpp:82-83
 
 
+@pytest.mark.parametrize("C,H,W", [(32, 144, 240), (64, 72, 120), (96, 36, 60), (128, 18, 28), (36, 11, 44), (8, 9, 12),
+                                   (20, 13, 50), (7, 5, 3)])
+def test_corr2d_backward_levels_vs_oracle(C, H, W, monkeypatch):
+    """a2 at the pyramid shapes: the register-tiled kernel (md = 4, C % 4 == 0, W % 4 == 0) and the simple one (other
+    shapes, or B200_CORR2D_BWD_SIMPLE=1) against the CPU oracle; ragged tiles and tiles larger than the map included."""
+    rng = np.random.default_rng(C * H + W)
+    f1 = rng.standard_normal((2, H, W, C), dtype=np.float32)
+    f2 = rng.standard_normal((2, H, W, C), dtype=np.float32)
+    go = rng.standard_normal((2, 81, H, W), dtype=np.float32)
+    w1, w2 = spec.corr2d_bwd(go, f1, f2, 4)
+    g1, g2 = b200.ops._correlation_backward_cuda(cu(go), cu(f1), cu(f2), 4)
+    np.testing.assert_allclose(g1.cpu().numpy(), w1, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(g2.cpu().numpy(), w2, rtol=1e-5, atol=1e-5)
+    monkeypatch.setenv("B200_CORR2D_BWD_SIMPLE", "1")
+    s1, s2 = b200.ops._correlation_backward_cuda(cu(go), cu(f1), cu(f2), 4)
+    torch.testing.assert_close(g1, s1, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(g2, s2, rtol=1e-5, atol=1e-5)
+
+
 def test_corr2d_kat_reference_test_main():
     """KAT-corr (correlation_test.cpp:44-60,82-89): rand B=32,C=128,144x240, md=4; fwd + both grads, mean|d|<1e-6.
     Inputs drawn on the CPU generator (the reference draws on the device, which is not reproducible)."""
