@@ -21,6 +21,7 @@ grid_sample is fused) + 25 stand-alone grid_sample_wrapper (the 83-channel one i
 attention, flow heads) is out of scope, so the feature maps the ops consume are synthetic activations.
 """
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -182,7 +183,7 @@ class CostVolumeStack:
             self.corr3d[lvl] = {n: v.to(self.device) for n, v in pwc3d.pack_weights(mod).items()}
         self._grids = {}
         self.concurrent = True        # independent op groups on side streams (parallel branches under graph capture)
-        self.max_streams = 6
+        self.max_streams = int(os.environ.get("B200_MAX_STREAMS", "6"))
 
     def pixel_grid(self, batch, h, w):
         key = (batch, h, w)
