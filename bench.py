@@ -214,7 +214,7 @@ def run_reference_arm(args, cfg, meta):
     }
     if note:
         line["note"] = note
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(cfg, batch, args):
@@ -227,8 +227,27 @@ def workload_config(cfg, batch, args):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner with printf on
+    file descriptor 1), so the real stdout is kept aside for the JSON line and descriptor 1 is pointed at stderr."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    _claim_stdout()
     meta = baseline_meta()
     from rpeflow_b200.stack import CONFIGS
     cfg = CONFIGS[args.workload]
@@ -247,8 +266,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL's debug stream (the "NCCL version ..." banner is printed at every
+        # level >= VERSION, WARN included) goes to stderr instead of its default, stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -468,7 +488,7 @@ def main():
         }
         if verify:
             line["verify"] = verify
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
