@@ -54,7 +54,7 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
                         const float* __restrict__ W1cT, const float* __restrict__ b2, const float* __restrict__ Wa,
                         const float* __restrict__ ba, const float* __restrict__ Wb, const float* __restrict__ bb,
                         const float* __restrict__ WcT, const float* __restrict__ bc, float* __restrict__ P,
-                        int Cout, int N1, int N2, uint32_t tmem_cols) {
+                        int Cout, int N1, int N2, uint32_t tmem_cols, int tiles_per_cta) {
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t sbase = (tc_smem_u32(tc_smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = tc_smem_raw + (sbase - tc_smem_u32(tc_smem_raw));
@@ -67,7 +67,7 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + L.bars + 24);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y, i0 = blockIdx.x * (TC_ROWS / TC_K);
+    const int b = blockIdx.y;
 
     if (tid == 0) {
         tc_mbar_init(bar_free, 1);
@@ -78,6 +78,30 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+
+    // per-CTA constants: epilogue table, W1c; then the tensor-memory base address
+    for (int o = tid; o < Cout; o += TC_THREADS) {
+        float* e = s_epi + o * 12;
+        e[0] = __ldg(b2 + o); e[1] = __ldg(bc + o); e[2] = 0.0f; e[3] = 0.0f;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) e[4 + m] = __ldg(WcT + (size_t)m * Cout + o);
+    }
+    for (int e = tid; e < 3 * Cout; e += TC_THREADS) s_w1c[e] = __ldg(W1cT + e);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    const int nkb = Cout / TC_KB;
+    const uint32_t idesc = umma_idesc_tf32(TC_ROWS, Cout);
+    const int q = lane & 7;                            // 16-byte chunk (4 channels) of the 128-byte row this lane handles
+    uint32_t it = 0;                                   // MMA batches committed to bar_free so far (its phase counter)
+
+    // A CTA walks `tiles_per_cta` consecutive tiles: the tensor-memory allocation, the barriers, the constants above and
+    // (when Cout = 32, a single K block) the W2 tile are set up once, not once per 8 points.
+    for (int tt = 0; tt < tiles_per_cta; ++tt) {
+    const int i0 = (blockIdx.x * tiles_per_cta + tt) * (TC_ROWS / TC_K);
+    if (i0 >= N1) break;
 
     // ---- meta: thread r owns row r = (point r/16, neighbour r%16)
     float hid[8];
@@ -92,25 +116,12 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
         s_d[tid] = make_float4(dx, dy, dz, 0.0f);
         weight_net_hidden(Wa, ba, Wb, bb, dx, dy, dz, hid);
     }
-    for (int o = tid; o < Cout; o += TC_THREADS) {
-        float* e = s_epi + o * 12;
-        e[0] = __ldg(b2 + o); e[1] = __ldg(bc + o); e[2] = 0.0f; e[3] = 0.0f;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) e[4 + m] = __ldg(WcT + (size_t)m * Cout + o);
-    }
-    for (int e = tid; e < 3 * Cout; e += TC_THREADS) s_w1c[e] = __ldg(W1cT + e);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *tmem_slot_ptr;
+    __syncthreads();                                   // s_j / s_d of this tile are visible to the gathering lanes
 
     // ---- K loop: produce a stage, one thread issues its MMAs
-    const int nkb = Cout / TC_KB;
-    const uint32_t idesc = umma_idesc_tf32(TC_ROWS, Cout);
-    const int q = lane & 7;                            // 16-byte chunk (4 channels) of the 128-byte row this lane handles
-    for (int kb = 0; kb < nkb; ++kb) {
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
         constexpr int st = 0;
-        if (kb >= 1) tc_mbar_wait(bar_free, (uint32_t)((kb - 1) & 1));   // the MMAs that read the stage are done
+        if (it >= 1) tc_mbar_wait(bar_free, (it - 1) & 1u);               // the MMAs that read the stage are done
         const uint32_t stage = sbase;
         const int c0 = kb * TC_KB + 4 * q;
         const float4 wx = *reinterpret_cast<const float4*>(s_w1c + c0);
@@ -138,6 +149,7 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
                 *reinterpret_cast<float4*>(gbase + st * L.stage_bytes + L.a_hi + off) = v;
             }
         }
+        if (nkb > 1 || tt == 0)                                // a single K block: the W2 tile of the first tile stays valid
         for (int e = tid; e < Cout * 8; e += TC_THREADS) {     // W2[o][kb*32 .. +32): the B operand, K-major
             const int o = e >> 3, qq = e & 7;
             const float4 v = __ldg(reinterpret_cast<const float4*>(W2 + (size_t)o * Cout + kb * TC_KB + 4 * qq));
@@ -169,7 +181,7 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
             if (kb == nkb - 1) umma_commit(bar_done);
         }
     }
-    tc_mbar_wait(bar_done, 0u);                        // accumulator complete
+    tc_mbar_wait(bar_done, (uint32_t)(tt & 1));        // accumulator complete (one commit per tile)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: thread = row (TMEM lane), 32 columns at a time
@@ -206,9 +218,12 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
         }
         if (pt < N1) *reinterpret_cast<float2*>(prow + cb + 2 * m) = make_float2(v[0], v[1]);
     }
-
+    // every warp has read its accumulator rows before the next tile's first MMA overwrites them (and before s_j / s_d change)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }   // tiles of this CTA
+
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
 }
 
@@ -227,20 +242,22 @@ cudaError_t corr3d_stage1_tc(const float* xyz1, const float* xyz2, const int64_t
     const size_t smem = (size_t)tc_layout(Cout, split).total + 1024;
     uint32_t cols = 32;
     while ((int)cols < Cout) cols <<= 1;
-    dim3 grid(ceil_div(N1, TC_ROWS / TC_K), B);
+    const int tiles = ceil_div(N1, TC_ROWS / TC_K);
+    const int tpc = tiles >= 128 ? 4 : (tiles >= 32 ? 2 : 1);      // tiles per CTA: amortise the per-CTA set-up, keep >= 16 CTAs per sample
+    dim3 grid(ceil_div(tiles, tpc), B);
     cudaError_t e;
     if (split) {
         e = cudaFuncSetAttribute(corr3d_stage1_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         corr3d_stage1_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(xyz1, xyz2, knn12, s.A1, s.G2, w->W2, s.W1cT, w->b2, w->n2_Wa,
                                                                    w->n2_ba, w->n2_Wb, w->n2_bb, s.n2WcT, w->n2_bc, s.P, Cout, N1,
-                                                                   N2, cols);
+                                                                   N2, cols, tpc);
     } else {
         e = cudaFuncSetAttribute(corr3d_stage1_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         corr3d_stage1_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(xyz1, xyz2, knn12, s.A1, s.G2, w->W2, s.W1cT, w->b2, w->n2_Wa,
                                                                    w->n2_ba, w->n2_Wb, w->n2_bb, s.n2WcT, w->n2_bc, s.P, Cout, N1,
-                                                                   N2, cols);
+                                                                   N2, cols, tpc);
     }
     return cudaGetLastError();
 }
