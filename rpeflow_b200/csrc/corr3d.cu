@@ -227,7 +227,10 @@ corr3d_stage2_kernel(const float* __restrict__ xyz1, const int64_t* __restrict__
     float* hid = smem;                                   // [rows][8]
     int* jj = reinterpret_cast<int*>(hid + (size_t)rows * 8);
     float* tile = reinterpret_cast<float*>(jj + rows);   // [Cout][33]
+    __shared__ __align__(16) float s_wn[WN_FLOATS];
     const int b = blockIdx.y, i0 = blockIdx.x * 32, tid = threadIdx.x;
+    weight_net_stage(s_wn, Wa, ba, Wb, bb, tid, 256);
+    __syncthreads();
 
     for (int r = tid; r < rows; r += 256) {
         const int pt = r / k, i = min(i0 + pt, N1 - 1);
@@ -237,7 +240,7 @@ corr3d_stage2_kernel(const float* __restrict__ xyz1, const int64_t* __restrict__
         const float dy = __ldg(xyz1 + ((size_t)b * 3 + 1) * N1 + j) - __ldg(xyz1 + ((size_t)b * 3 + 1) * N1 + i);
         const float dz = __ldg(xyz1 + ((size_t)b * 3 + 2) * N1 + j) - __ldg(xyz1 + ((size_t)b * 3 + 2) * N1 + i);
         jj[r] = (int)j;
-        weight_net_hidden(Wa, ba, Wb, bb, dx, dy, dz, hid + r * 8);
+        weight_net_hidden_s(s_wn, dx, dy, dz, hid + r * 8);
     }
     __syncthreads();
 
@@ -248,12 +251,14 @@ corr3d_stage2_kernel(const float* __restrict__ xyz1, const int64_t* __restrict__
         for (int m = 0; m < 8; ++m) wc[m] = __ldg(WcT + (size_t)m * Cout + o);
         const float bco = __ldg(bc + o);
         float sum = 0.0f;
+#pragma unroll 4
         for (int s = 0; s < k; ++s) {
             const int r = pt * k + s;
-            const float* hd = hid + (size_t)r * 8;
+            const float4 h0 = *reinterpret_cast<const float4*>(hid + (size_t)r * 8);          // warp-wide broadcast reads
+            const float4 h1 = *reinterpret_cast<const float4*>(hid + (size_t)r * 8 + 4);
             float w = bco;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) w = fmaf(wc[m], hd[m], w);
+            w = fmaf(wc[0], h0.x, w); w = fmaf(wc[1], h0.y, w); w = fmaf(wc[2], h0.z, w); w = fmaf(wc[3], h0.w, w);
+            w = fmaf(wc[4], h1.x, w); w = fmaf(wc[5], h1.y, w); w = fmaf(wc[6], h1.z, w); w = fmaf(wc[7], h1.w, w);
             sum = fmaf(fmaxf(w, 0.0f), __ldg(P + ((size_t)b * N1 + jj[r]) * Cout + o), sum);   // row gather, coalesced over o
         }
         tile[o * 33 + pt] = sum;

@@ -26,7 +26,7 @@ namespace b200 {
 constexpr int TC_ROWS = 128, TC_KB = 32, TC_THREADS = 128, TC_K = 16;   // TC_K: neighbours per point this kernel is built for
 
 struct TcSmem {                      // byte offsets from the 1024-aligned base
-    int a_hi, a_lo, w_hi, w_lo, stage_bytes, epi, w1c, meta_j, meta_d, bars, total;
+    int a_hi, a_lo, w_hi, w_lo, stage_bytes, epi, w1c, wn, meta_j, meta_d, bars, total;
 };
 __host__ __device__ inline TcSmem tc_layout(int Cout, int split) {
     TcSmem L;
@@ -39,6 +39,7 @@ __host__ __device__ inline TcSmem tc_layout(int Cout, int split) {
     int off = L.stage_bytes;                           // one stage: co-resident CTAs (not a ring) hide the gather latency
     L.epi = off;     off += Cout * 48;                 // per output channel: b2, bc, -, -, Wc[0..7]
     L.w1c = off;     off += 3 * Cout * 4;
+    L.wn = off;      off += WN_FLOATS * 4;              // weight net parameters (16-byte aligned: Cout % 32 == 0)
     L.meta_j = off;  off += TC_ROWS * 4;
     L.meta_d = off;  off += TC_ROWS * 16;
     off = (off + 15) & ~15;
@@ -61,6 +62,7 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
     const TcSmem L = tc_layout(Cout, SPLIT);
     float* s_epi = reinterpret_cast<float*>(gbase + L.epi);
     float* s_w1c = reinterpret_cast<float*>(gbase + L.w1c);
+    float* s_wn = reinterpret_cast<float*>(gbase + L.wn);
     int* s_j = reinterpret_cast<int*>(gbase + L.meta_j);
     float4* s_d = reinterpret_cast<float4*>(gbase + L.meta_d);
     const uint32_t bar_free = sbase + L.bars, bar_done = bar_free + 16, tmem_slot = bar_free + 24;
@@ -87,6 +89,7 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
         for (int m = 0; m < 8; ++m) e[4 + m] = __ldg(WcT + (size_t)m * Cout + o);
     }
     for (int e = tid; e < 3 * Cout; e += TC_THREADS) s_w1c[e] = __ldg(W1cT + e);
+    weight_net_stage(s_wn, Wa, ba, Wb, bb, tid, TC_THREADS);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -114,7 +117,7 @@ corr3d_stage1_tc_kernel(const float* __restrict__ xyz1, const float* __restrict_
         const float dz = __ldg(xyz2 + ((size_t)b * 3 + 2) * N2 + j) - __ldg(xyz1 + ((size_t)b * 3 + 2) * N1 + i);
         s_j[tid] = (int)j;
         s_d[tid] = make_float4(dx, dy, dz, 0.0f);
-        weight_net_hidden(Wa, ba, Wb, bb, dx, dy, dz, hid);
+        weight_net_hidden_s(s_wn, dx, dy, dz, hid);
     }
     __syncthreads();                                   // s_j / s_d of this tile are visible to the gathering lanes
 
