@@ -340,7 +340,14 @@ project_nn_corr_kernel(const float* __restrict__ xy, const float* __restrict__ f
                 acc += sv.z * __ldg(f + (size_t)(c + 2) * HW);
                 acc += sv.w * __ldg(f + (size_t)(c + 3) * HW);
             }
-        } else {
+        } else {                                                        // rows of S are not 16-byte aligned (C2 = 81: the cost volume)
+            for (; c + 8 <= C2; c += 8) {                               // same order of accumulation, 16 loads in flight
+                float sv[8], v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { sv[u] = __ldg(s + c + u); v[u] = __ldg(f + (size_t)(c + u) * HW); }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += sv[u] * v[u];
+            }
             for (; c < C2; ++c) acc += __ldg(s + c) * __ldg(f + (size_t)c * HW);
         }
         o[(size_t)2 * HW] = __fdiv_rn(acc, (float)C2);                  // torch.mean over channels
