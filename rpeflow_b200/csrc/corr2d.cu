@@ -274,7 +274,7 @@ static cudaError_t launch_corr2d_bwd(const float* gout, const float* in1, const 
 extern "C" int b200_corr2d_fwd(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int md,
                                b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(in1 && in2 && out, "b200_corr2d_fwd: null pointer");
+    B200_REQUIRE((B == 0) || (in1 && in2 && out), "b200_corr2d_fwd: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "b200_corr2d_fwd: bad sizes B=%d C=%d H=%d W=%d", B, C, H, W);
     B200_REQUIRE(md >= 1 && md <= 4, "b200_corr2d_fwd: max_displacement must be in [1,4] (got %d)", md);
     if (B == 0) return B200_OK;
@@ -297,7 +297,7 @@ extern "C" int b200_corr2d_fwd(const float* in1, const float* in2, float* out, i
 extern "C" int b200_corr2d_bwd(const float* gout, const float* in1, const float* in2, float* gin1, float* gin2,
                                int B, int C, int H, int W, int md, b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(gout && in1 && in2 && gin1 && gin2, "b200_corr2d_bwd: null pointer");
+    B200_REQUIRE((B == 0) || (gout && in1 && in2 && gin1 && gin2), "b200_corr2d_bwd: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "b200_corr2d_bwd: bad sizes B=%d C=%d H=%d W=%d", B, C, H, W);
     B200_REQUIRE(md >= 1 && md <= 4, "b200_corr2d_bwd: max_displacement must be in [1,4] (got %d)", md);
     B200_REQUIRE(H <= 65535 && B <= 65535, "b200_corr2d_bwd: H or B exceeds the grid limit");

@@ -296,7 +296,7 @@ extern "C" int b200_corr3d_fwd(const float* xyz1, const float* feat1, const floa
                                float* scratch, int B, int Cin, int Cout, int N1, int N2, int k, int precision,
                                b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(xyz1 && feat1 && xyz2 && feat2 && knn12 && knn11 && w && out && scratch, "b200_corr3d_fwd: null pointer");
+    B200_REQUIRE((B == 0) || (xyz1 && feat1 && xyz2 && feat2 && knn12 && knn11 && w && out && scratch), "b200_corr3d_fwd: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && Cin >= 1 && Cout >= 1 && N1 >= 1 && N2 >= 1, "b200_corr3d_fwd: bad sizes");
     B200_REQUIRE(k >= 1 && k <= 32, "b200_corr3d_fwd: k must be in [1,32] (got %d)", k);
     B200_REQUIRE(Cout <= 512, "b200_corr3d_fwd: Cout=%d exceeds 512", Cout);

@@ -376,7 +376,7 @@ static cudaError_t dispatch_ppt(const float* xyz, int64_t* idx, int B, int N, in
 
 extern "C" int b200_fps(const float* xyz, int64_t* idx, int B, int N, int n_samples, b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(xyz && idx, "b200_fps: null pointer");
+    B200_REQUIRE((B == 0) || (xyz && idx), "b200_fps: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && n_samples >= 1, "b200_fps: bad sizes B=%d n_samples=%d", B, n_samples);
     B200_REQUIRE(N > n_samples, "b200_fps: need N > n_samples (N=%d, n_samples=%d) as models/csrc/wrapper.py:98", N, n_samples);
     if (N > 8 * 8192) {

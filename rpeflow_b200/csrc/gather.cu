@@ -428,7 +428,7 @@ static int pick_csplit(int64_t cols, int B, int C) {
 extern "C" int b200_gather_cf(const void* data, const int64_t* idx, void* out, int B, int C, int N, int64_t I,
                               int* bad_count, b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(data && idx && out, "b200_gather_cf: null pointer");
+    B200_REQUIRE((B == 0 || C == 0 || I == 0) || (data && idx && out), "b200_gather_cf: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C >= 0 && N >= 1 && I >= 0, "b200_gather_cf: bad sizes");
     B200_REQUIRE(B <= 65535, "b200_gather_cf: B exceeds the grid limit");
     if (B == 0 || C == 0 || I == 0) return B200_OK;
@@ -441,7 +441,7 @@ extern "C" int b200_gather_cf(const void* data, const int64_t* idx, void* out, i
 extern "C" int b200_gather_cl(const void* data, const int64_t* idx, void* out, int B, int C, int N, int64_t I,
                               int* bad_count, b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(data && idx && out, "b200_gather_cl: null pointer");
+    B200_REQUIRE((B == 0 || C == 0 || I == 0) || (data && idx && out), "b200_gather_cl: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C >= 0 && N >= 1 && I >= 0, "b200_gather_cl: bad sizes");
     B200_REQUIRE(B <= 65535, "b200_gather_cl: B exceeds the grid limit");
     if (B == 0 || C == 0 || I == 0) return B200_OK;
@@ -457,7 +457,7 @@ extern "C" int b200_gather_cl(const void* data, const int64_t* idx, void* out, i
 extern "C" int b200_grid_sample_pts(const float* feat, const float* xy, float* out, int B, int C, int H, int W, int N,
                                     b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(feat && xy && out, "b200_grid_sample_pts: null pointer");
+    B200_REQUIRE((B == 0 || C == 0 || N == 0) || (feat && xy && out), "b200_grid_sample_pts: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1 && N >= 0, "b200_grid_sample_pts: bad sizes");
     B200_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, "b200_grid_sample_pts: plane or batch too large");
     if (B == 0 || C == 0 || N == 0) return B200_OK;
@@ -470,7 +470,7 @@ extern "C" int b200_grid_sample_pts(const float* feat, const float* xy, float* o
 
 extern "C" int b200_backwarp2d(const float* x, const float* flow, float* out, int B, int C, int H, int W, b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(x && flow && out, "b200_backwarp2d: null pointer");
+    B200_REQUIRE((B == 0 || C == 0) || (x && flow && out), "b200_backwarp2d: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1, "b200_backwarp2d: bad sizes");
     B200_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, "b200_backwarp2d: plane or batch too large");
     if (B == 0 || C == 0) return B200_OK;
@@ -485,7 +485,7 @@ extern "C" int b200_backwarp2d(const float* x, const float* flow, float* out, in
 extern "C" int b200_convex_upsample(const float* flow, const float* mask, float* out, int B, int H, int W, int scale,
                                     b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(flow && mask && out, "b200_convex_upsample: null pointer");
+    B200_REQUIRE((B == 0) || (flow && mask && out), "b200_convex_upsample: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && H >= 1 && W >= 1, "b200_convex_upsample: bad sizes");
     B200_REQUIRE(scale == 2 || scale == 4 || scale == 8, "b200_convex_upsample: scale_factor must be 2, 4 or 8 (got %d)", scale);
     B200_REQUIRE((int64_t)H * W * scale * scale < (1ll << 31) && B <= 65535, "b200_convex_upsample: plane or batch too large");
@@ -504,7 +504,7 @@ extern "C" int b200_project_nn_corr(const float* xy, const float* feat2d, const 
                                     float* out, float* scratch, int B, int C2, int C3, int H, int W, int N,
                                     b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(xy && feat2d && feat3d && nn && out && scratch, "b200_project_nn_corr: null pointer");
+    B200_REQUIRE((B == 0) || (xy && feat2d && feat3d && nn && out && scratch), "b200_project_nn_corr: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C2 >= 1 && C3 >= 0 && H >= 1 && W >= 1 && N >= 1, "b200_project_nn_corr: bad sizes");
     B200_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, "b200_project_nn_corr: plane or batch too large");
     B200_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "b200_project_nn_corr: scratch must be 16-byte aligned");
@@ -522,7 +522,7 @@ extern "C" int b200_knn_interpolate(const float* input_xyz, const float* input_f
                                     const int64_t* knn_idx, float* out, int B, int C, int M, int Q, int k,
                                     b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(input_xyz && input_feat && query_xyz && knn_idx && out, "b200_knn_interpolate: null pointer");
+    B200_REQUIRE((B == 0 || C == 0 || Q == 0) || (input_xyz && input_feat && query_xyz && knn_idx && out), "b200_knn_interpolate: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C >= 0 && M >= 1 && Q >= 0, "b200_knn_interpolate: bad sizes");
     B200_REQUIRE(k >= 1 && k <= KI_KMAX, "b200_knn_interpolate: k must be in [1,%d] (got %d)", KI_KMAX, k);
     B200_REQUIRE(B <= 65535, "b200_knn_interpolate: B exceeds the grid limit");

@@ -204,7 +204,7 @@ static void launch_knn(const float* input, const float* query, int64_t* idx, int
 extern "C" int b200_knn(const float* input_xyz, const float* query_xyz, int64_t* idx,
                         int B, int M, int Q, int D, int k, b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(input_xyz && query_xyz && idx, "b200_knn: null pointer");
+    B200_REQUIRE((B == 0 || Q == 0) || (input_xyz && query_xyz && idx), "b200_knn: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(D == 2 || D == 3, "b200_knn: D must be 2 or 3 (got %d)", D);
     B200_REQUIRE(k >= 1 && k <= 32, "b200_knn: k must be in [1,32] (got %d); the reference kernel has 32 slots", k);
     B200_REQUIRE(B >= 0 && M >= 1 && Q >= 0, "b200_knn: bad sizes B=%d M=%d Q=%d", B, M, Q);

@@ -528,7 +528,7 @@ extern "C" int64_t b200_knn_scratch_bytes(int B, int M, int Q, int D, int k) {
 extern "C" int b200_knn_grid(const float* input_xyz, const float* query_xyz, int64_t* idx, void* scratch,
                              int64_t scratch_bytes, int B, int M, int Q, int D, int k, b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(input_xyz && query_xyz && idx && scratch, "b200_knn_grid: null pointer");
+    B200_REQUIRE((B == 0 || Q == 0) || (input_xyz && query_xyz && idx && scratch), "b200_knn_grid: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(D == 2 || D == 3, "b200_knn_grid: D must be 2 or 3 (got %d)", D);
     B200_REQUIRE(k >= 1 && k <= 32, "b200_knn_grid: k must be in [1,32] (got %d); the reference kernel has 32 slots", k);
     B200_REQUIRE(B >= 0 && M >= 1 && Q >= 0, "b200_knn_grid: bad sizes B=%d M=%d Q=%d", B, M, Q);

@@ -274,7 +274,7 @@ extern "C" int b200_pointconv_fwd(const float* xyz, const float* feat, const flo
                                   const b200_pointconv_weights* w, float* out, float* scratch, int B, int C, int Cout,
                                   int N, int S, int k, int precision, b200_stream_t stream) {
     using namespace b200;
-    B200_REQUIRE(xyz && sampled_xyz && knn && w && out && scratch && (feat || C == 0), "b200_pointconv_fwd: null pointer");
+    B200_REQUIRE((B == 0 || S == 0) || (xyz && sampled_xyz && knn && w && out && scratch && (feat || C == 0)), "b200_pointconv_fwd: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(w->Wa && w->ba && w->Wb && w->bb && w->L && w->bias, "b200_pointconv_fwd: null weight pointer");
     B200_REQUIRE(B >= 0 && C >= 0 && Cout >= 1 && N >= 1 && S >= 0, "b200_pointconv_fwd: bad sizes");
     B200_REQUIRE(B <= 65535, "b200_pointconv_fwd: B exceeds the grid limit");

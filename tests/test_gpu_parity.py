@@ -653,6 +653,27 @@ def test_convex_upsample_vs_oracle(B, H, W, s):
         b200.convex_upsample(flow, mask, s)                                                  # CPU tensors: no fallback
 
 
+# ------------------------------------------------------------------------------------------------- empty inputs
+def test_empty_batches_and_queries():
+    """Batch 0 / zero queries: every entry point returns a correctly shaped empty result (torch semantics; the reference's
+    unchecked zero-size launches end the same way)."""
+    z = lambda *shape: torch.zeros(shape, device=DEV)
+    assert b200.correlation2d(z(0, 8, 12, 16), z(0, 8, 12, 16), 4).shape == (0, 81, 12, 16)
+    assert b200.ops._correlation_forward_cuda(z(0, 12, 16, 8), z(0, 12, 16, 8), 4).shape == (0, 81, 12, 16)
+    g1, g2 = b200.ops._correlation_backward_cuda(z(0, 81, 12, 16), z(0, 12, 16, 8), z(0, 12, 16, 8), 4)
+    assert g1.shape == (0, 8, 12, 16) and g2.shape == (0, 8, 12, 16)
+    assert b200.ops._furthest_point_sampling_cuda(z(0, 100, 3), 10).shape == (0, 10)
+    assert b200.ops._k_nearest_neighbor_cuda(z(0, 50, 3), z(0, 20, 3), 4).shape == (0, 20, 4)
+    assert b200.ops._k_nearest_neighbor_cuda(torch.rand(2, 50, 3, device=DEV), z(2, 0, 3), 4).shape == (2, 0, 4)
+    assert b200.grid_sample_wrapper(z(0, 4, 6, 8), z(0, 2, 5)).shape == (0, 4, 5)
+    assert b200.grid_sample_wrapper(torch.rand(2, 4, 6, 8, device=DEV), z(2, 2, 0)).shape == (2, 4, 0)
+    assert b200.backwarp_2d(z(0, 4, 6, 8), z(0, 2, 6, 8)).shape == (0, 4, 6, 8)
+    assert b200.convex_upsample(z(0, 2, 3, 4), z(0, 144, 3, 4), 4).shape == (0, 2, 12, 16)
+    assert b200.batch_indexing_channel_first(z(0, 4, 9), torch.zeros(0, 5, dtype=torch.int64, device=DEV)).shape == (0, 4, 5)
+    with pytest.raises((RuntimeError, IndexError)):                 # the reference indexes events[-1]: no events is an error there too
+        b200_events.events_to_voxel_device(z(0, 4), 5, 6, 8, True)
+
+
 # ------------------------------------------------------------------------------------------------- PointConv (§8f rank 1)
 @pytest.mark.parametrize("precision,tol", [(2, 1e-4), (1, 5e-3)])
 @pytest.mark.parametrize("tag", ["down", "nosample"])
