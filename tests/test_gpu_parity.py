@@ -674,6 +674,36 @@ def test_empty_batches_and_queries():
         b200_events.events_to_voxel_device(z(0, 4), 5, 6, 8, True)
 
 
+# ------------------------------------------------------------------------------------------------- wrapper-level behaviour
+def test_wrapper_level_views_and_dtypes():
+    """The python mirrors accept what the reference wrappers accept: non-contiguous views, float64 feature maps
+    (wrapper.py:68-69 casts to float), channel-first or channel-last clouds (wrapper.py:108-115), any int index dtype."""
+    g = torch.Generator().manual_seed(21)
+    f1 = torch.randn(2, 16, 24, 32, generator=g).to(DEV)
+    f2 = torch.randn(2, 16, 24, 32, generator=g).to(DEV)
+    base = b200.correlation2d(f1, f2, 4)
+    nhwc1, nhwc2 = f1.permute(0, 2, 3, 1).contiguous(), f2.permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(b200.correlation2d(nhwc1.permute(0, 3, 1, 2), nhwc2.permute(0, 3, 1, 2), 4), base)   # permuted views
+    torch.testing.assert_close(b200.correlation2d(f1.double(), f2.double(), 4), base, rtol=1e-6, atol=1e-6)
+    assert b200.correlation2d(f1.double(), f2.double(), 4).dtype == torch.float32
+    pts = torch.rand(2, 500, 3, generator=g).to(DEV)
+    qry = torch.rand(2, 70, 3, generator=g).to(DEV)
+    cl = b200.k_nearest_neighbor(pts, qry, 8)
+    cf = b200.k_nearest_neighbor(pts.transpose(1, 2), qry.transpose(1, 2), 8)                  # [B,3,M]: auto-transposed
+    assert torch.equal(cl, cf)
+    assert torch.equal(b200.k_nearest_neighbor(pts.transpose(1, 2).contiguous(), qry.transpose(1, 2).contiguous(), 8), cl)
+    data = torch.randn(2, 5, 500, generator=g).to(DEV)
+    want = b200.batch_indexing_channel_first(data, cl)
+    assert torch.equal(b200.batch_indexing_channel_first(data, cl.to(torch.int32)), want)
+    ref = torch.gather(data.unsqueeze(2).expand(-1, -1, 70, -1), 3, cl.unsqueeze(1).expand(-1, 5, -1, -1))   # [B,C,Q,k]
+    assert torch.equal(want, ref)
+    xy = (torch.rand(2, 70, 2, generator=g) * torch.tensor([31.0, 23.0])).to(DEV)
+    a = b200.grid_sample_wrapper(f1, xy.transpose(1, 2))                                       # non-contiguous [B,2,N] view
+    assert torch.equal(a, b200.grid_sample_wrapper(f1, xy.transpose(1, 2).contiguous()))
+    flow = torch.randn(2, 24, 32, 2, generator=g).to(DEV)
+    assert torch.equal(b200.backwarp_2d(f2, flow.permute(0, 3, 1, 2)), b200.backwarp_2d(f2, flow.permute(0, 3, 1, 2).contiguous()))
+
+
 # ------------------------------------------------------------------------------------------------- PointConv (§8f rank 1)
 @pytest.mark.parametrize("precision,tol", [(2, 1e-4), (1, 5e-3)])
 @pytest.mark.parametrize("tag", ["down", "nosample"])
