@@ -600,7 +600,8 @@ def test_warp2d_golden(golden):
         b200.backwarp_2d(torch.from_numpy(g["f2"]), torch.from_numpy(g["flow"]))               # CPU tensors: no fallback
 
 
-@pytest.mark.parametrize("B,C,H,W", [(3, 32, 144, 240), (2, 64, 72, 120), (2, 96, 36, 60), (1, 5, 9, 16), (2, 33, 18, 28)])
+@pytest.mark.parametrize("B,C,H,W", [(3, 32, 144, 240), (2, 64, 72, 120), (2, 96, 36, 60), (1, 5, 9, 16), (2, 33, 18, 28),
+                                     (1, 1, 1, 4), (1, 3, 2, 8), (1, 8, 70, 52), (1, 12, 5, 100)])
 def test_warp_correlate_vs_oracle(B, C, H, W):
     """Level shapes of config 1 (both corr2d tilings) and ragged ones; flows large enough to leave the image."""
     gen = torch.Generator().manual_seed(H * W + C)
