@@ -163,6 +163,15 @@ B200_API int b200_project_nn_corr(const float* xy, const float* feat2d_nchw, con
                          const int64_t* nn, float* out, float* scratch,
                          int B, int C2, int C3, int H, int W, int N, b200_stream_t stream);
 
+/* a8 + a7 in one pass.  Same as b200_project_nn_corr; additionally, when sampled_cf != NULL, writes
+ *   sampled_cf [B,C2,N] = bilinear(feat2d, xy)   == grid_sample_wrapper(feat2d, xy) (models/utils.py:288-294),
+ * the tensor the 2D->3D fuser asks for right after the 3D->2D one with the same map and points
+ * (models/RPEFlow_core.py:31+53, :80+107, :134+157): the feature map is sampled once, not twice.
+ */
+B200_API int b200_project_nn_corr_sampled(const float* xy, const float* feat2d_nchw, const float* feat3d,
+                         const int64_t* nn, float* out, float* scratch, float* sampled_cf,
+                         int B, int C2, int C3, int H, int W, int N, b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * f1  PointConv forward, both PointConvDownSampling and PointConvNoSampling (= sampled_xyz is xyz).
  * Replaces: models/pointconv.py:33-61 and :90-122 after their k_nearest_neighbor call (gathers, weight net,

@@ -264,9 +264,13 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
 
 // a8, pass 1: S[b,n,c] = bilinear(feat2d[b,c], xy[b,:,n])  (point-major scratch).  Block = 16 points; compute: a warp
 // owns 4 of every 32 channels, lanes = 16 points x 2 tap sides (see half_taps); write: lane = channel (contiguous in S).
+// cf (optional): the same samples channel-first [B,C,N] — exactly what grid_sample_wrapper(feat2d, xy) returns
+// (same taps, same arithmetic as grid_sample_pts_kernel), written as 64-byte runs from the compute lanes.  The model asks
+// for that tensor right after this call in four of its five fuser pairs per level (RPEFlow_core.py:31+53, :80+107,
+// :134+157), so sampling once here saves a second pass over the whole feature map.
 __global__ void __launch_bounds__(256)
 sample_point_major_kernel(const float* __restrict__ feat, const float* __restrict__ xy, float* __restrict__ S,
-                          int C, int H, int W, int N) {
+                          float* __restrict__ cf, int C, int H, int W, int N) {
     __shared__ float tile[32][17];
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * 16;
@@ -286,7 +290,10 @@ sample_point_major_kernel(const float* __restrict__ feat, const float* __restric
             const int c = c0 + tc * 4 + u;
             float v = c < C ? half_blend(f + (size_t)c * plane, h) : 0.0f;
             v += __shfl_xor_sync(FULL, v, 1);
-            if (side == 0) tile[tc * 4 + u][tp] = v;
+            if (side == 0) {
+                tile[tc * 4 + u][tp] = v;
+                if (cf != nullptr && ok && c < C) cf[((size_t)b * C + c) * N + n] = v;
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -503,6 +510,12 @@ extern "C" int b200_convex_upsample(const float* flow, const float* mask, float*
 extern "C" int b200_project_nn_corr(const float* xy, const float* feat2d, const float* feat3d, const int64_t* nn,
                                     float* out, float* scratch, int B, int C2, int C3, int H, int W, int N,
                                     b200_stream_t stream) {
+    return b200_project_nn_corr_sampled(xy, feat2d, feat3d, nn, out, scratch, nullptr, B, C2, C3, H, W, N, stream);
+}
+
+extern "C" int b200_project_nn_corr_sampled(const float* xy, const float* feat2d, const float* feat3d, const int64_t* nn,
+                                            float* out, float* scratch, float* sampled_cf, int B, int C2, int C3, int H,
+                                            int W, int N, b200_stream_t stream) {
     using namespace b200;
     B200_REQUIRE((B == 0) || (xy && feat2d && feat3d && nn && out && scratch), "b200_project_nn_corr: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C2 >= 1 && C3 >= 0 && H >= 1 && W >= 1 && N >= 1, "b200_project_nn_corr: bad sizes");
@@ -510,7 +523,7 @@ extern "C" int b200_project_nn_corr(const float* xy, const float* feat2d, const 
     B200_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "b200_project_nn_corr: scratch must be 16-byte aligned");
     if (B == 0) return B200_OK;
     cudaStream_t st = as_stream(stream);
-    sample_point_major_kernel<<<dim3(ceil_div(N, 16), B), 256, 0, st>>>(feat2d, xy, scratch, C2, H, W, N);
+    sample_point_major_kernel<<<dim3(ceil_div(N, 16), B), 256, 0, st>>>(feat2d, xy, scratch, sampled_cf, C2, H, W, N);
     B200_LAUNCH_CHECK("b200_project_nn_corr(sample)");
     project_nn_corr_kernel<<<dim3(ceil_div((int64_t)H * W, 256), B, 1 + ceil_div(C3, PN_SLAB)), 256, 0, st>>>(
         xy, feat2d, feat3d, nn, scratch, out, C2, C3, H, W, N);

@@ -52,6 +52,15 @@ def eventsToVoxel(events, num_bins=5, height=None, width=None, event_polarity=Fa
     """numpy [n,4] float (x,y,t,p) -> numpy [bins*(2|1),H,W] float32 (event_utils.py:109-128)."""
     if not temporal_bilinear:
         raise NotImplementedError("temporal_bilinear=False is not on the hot path (every caller uses the default)")
+    events = np.asarray(events)
+    if events.dtype != np.float32:
+        # The reference normalises (t - t0) / (dt + 1e-6) in the INPUT dtype (event_utils.py:30-34); float64 stamps with a
+        # large absolute value (microseconds since boot) would quantise if they were cast first.  Shift in the original
+        # dtype, then cast: the kernel's own (t - t_first) becomes a no-op on the already shifted stamps.
+        shifted = np.empty(events.shape, dtype=np.float32)
+        shifted[:, 0], shifted[:, 1], shifted[:, 3] = events[:, 0], events[:, 1], events[:, 3]
+        shifted[:, 2] = events[:, 2] - events[0, 2]
+        events = shifted
     events = np.ascontiguousarray(events, dtype=np.float32)
     if height is None or width is None:           # event_utils.py:116-118
         width = int(events[:, 0].astype(np.int32).max()) + 1

@@ -66,10 +66,57 @@ def batch_indexing_channel_last(batched_data, batched_indices):
     return out.view(shape) if flat else out.view(shape + [C])
 
 
+class _SampleMemo:
+    """Samples that project_feat_with_nn_corr(xy, feat_2d, ...) has already taken: bilinear(feat_2d, xy) as [B,C,N].
+
+    The model samples the same map at the same points twice in four of its five fuser pairs per level — the 3D->2D fuser
+    calls project_feat_with_nn_corr(xy, feat_2d, ...) and the 2D->3D fuser then calls grid_sample_wrapper(feat_2d, xy)
+    (RPEFlow_core.py:31+53, :80+107, :134+157).  The first call's sampler kernel writes that second result as a by-product
+    (b200_project_nn_corr_sampled); it is parked here and handed out ONCE to the next grid_sample_wrapper call with the
+    same (map, points).  An entry holds references to both key tensors — their storage cannot be recycled while it is
+    parked — and records their version counters, so an in-place write to either one invalidates it.  A handful of
+    entries (a level has four pairs in flight) bounds what is kept alive."""
+
+    def __init__(self, capacity=6):
+        self.capacity = capacity
+        self.entries = []
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _key(t):
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version)
+
+    def put(self, feat_2d, xy, sampled):
+        self.entries.append((feat_2d, self._key(feat_2d), xy, self._key(xy), sampled))
+        del self.entries[:-self.capacity]
+
+    def take(self, feat_2d, xy):
+        kf, kx = self._key(feat_2d), self._key(xy)
+        for i in range(len(self.entries) - 1, -1, -1):
+            f, f_key, x, x_key, sampled = self.entries[i]
+            if f_key == kf and x_key == kx and self._key(f) == kf and self._key(x) == kx:
+                del self.entries[i]
+                self.hits += 1
+                return sampled
+        self.misses += 1
+        return None
+
+    def clear(self):
+        self.entries.clear()
+
+
+SAMPLE_MEMO = _SampleMemo()
+
+
 def grid_sample_wrapper(feat_2d, xy):
-    """feat_2d [B,C,H,W], xy [B,2,N] (pixels) -> [B,C,N]; bilinear, align_corners=True, zero padding."""
+    """feat_2d [B,C,H,W], xy [B,2,N] (pixels) -> [B,C,N]; bilinear, align_corners=True, zero padding.
+    If project_feat_with_nn_corr has just sampled this very map at these very points, its result is returned
+    (see _SampleMemo) and no kernel runs."""
     if not (feat_2d.is_cuda and xy.is_cuda):
         raise RuntimeError("rpeflow_b200.grid_sample_wrapper: CUDA tensors required — no CPU/torch fallback")
+    parked = SAMPLE_MEMO.take(feat_2d, xy)
+    if parked is not None:
+        return parked
     feat = feat_2d.contiguous().float()
     pts = xy.contiguous().float()
     B, C, H, W = feat.shape
@@ -121,8 +168,10 @@ def convex_upsample(flow, mask, scale_factor=8):
 
 
 @torch.no_grad()
-def project_feat_with_nn_corr(xy, feat_2d, feat_3d, nn_indices=None):
-    """xy [B,2,N], feat_2d [B,C2,H,W], feat_3d [B,C3,N], nn_indices [B,H*W] -> [B,C3+3,H,W]."""
+def project_feat_with_nn_corr(xy, feat_2d, feat_3d, nn_indices=None, keep_samples=True):
+    """xy [B,2,N], feat_2d [B,C2,H,W], feat_3d [B,C3,N], nn_indices [B,H*W] -> [B,C3+3,H,W].
+    keep_samples: also keep bilinear(feat_2d, xy) as [B,C2,N] for the grid_sample_wrapper(feat_2d, xy) call that
+    follows in the model (one extra 4*C2*N-byte write instead of a second pass over the map)."""
     if not (xy.is_cuda and feat_2d.is_cuda and feat_3d.is_cuda):
         raise RuntimeError("rpeflow_b200.project_feat_with_nn_corr: CUDA tensors required — no CPU/torch fallback")
     f2 = feat_2d.contiguous().float()
@@ -141,9 +190,13 @@ def project_feat_with_nn_corr(xy, feat_2d, feat_3d, nn_indices=None):
     nn = _prep_idx(nn_indices, f2.device)
     out = torch.empty((B, C3 + 3, H, W), dtype=torch.float32, device=f2.device)
     scratch = torch.empty((B, N, C2), dtype=torch.float32, device=f2.device)
+    sampled = torch.empty((B, C2, N), dtype=torch.float32, device=f2.device) if keep_samples else None
     with torch.cuda.device(f2.device):
-        check(lib.b200_project_nn_corr(pts.data_ptr(), f2.data_ptr(), f3.data_ptr(), nn.data_ptr(), out.data_ptr(),
-                                       scratch.data_ptr(), B, C2, C3, H, W, N, _stream(f2)), "b200_project_nn_corr")
+        check(lib.b200_project_nn_corr_sampled(pts.data_ptr(), f2.data_ptr(), f3.data_ptr(), nn.data_ptr(), out.data_ptr(),
+                                               scratch.data_ptr(), sampled.data_ptr() if keep_samples else None,
+                                               B, C2, C3, H, W, N, _stream(f2)), "b200_project_nn_corr")
+    if keep_samples:
+        SAMPLE_MEMO.put(feat_2d, xy, sampled)
     return out
 
 

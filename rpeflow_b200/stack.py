@@ -20,134 +20,14 @@ danqu130/RPEFlow):
 grid_sample is fused) + 25 stand-alone grid_sample_wrapper (the 83-channel one is issued as 81 + 2 channels).  Everything between those calls (convolutions,
 attention, flow heads) is out of scope, so the feature maps the ops consume are synthetic activations.
 """
-import math
 import os
-from dataclasses import dataclass, field
 
 import torch
 
 from . import events as _events
 from . import ops, projection, pwc3d
-
-LEVEL_CHANNELS = [32, 64, 96, 128, 192]          # levels 1..5 (pwc2d_core.py:28-40 / pwc3d_core.py:44-57)
-PYRAMID_POINTS = [4096, 2048, 1024, 512, 256]    # RPEFlow.py:74 (hard-coded)
-
-
-@dataclass
-class StackConfig:
-    name: str = "things"          # "things" (cfg1, integer-pixel voxels) | "dsec" (cfg4, tri-linear voxels)
-    height: int = 540
-    width: int = 960
-    n_points: int = 8192
-    n_events: int = 1_000_000
-    event_bins: int = 10
-    k: int = 16
-    max_displacement: int = 4
-    focal: float = 1050.0
-    max_depth: float = 35.0
-    precision: int = 2            # Correlation3D arithmetic (include/b200flow.h): 2 = 3xTF32 on tcgen05, meets the fp32 bar
-
-    @property
-    def padded(self):             # resize_to_64x (models/utils.py:227-241)
-        return (self.height + 63) // 64 * 64, (self.width + 63) // 64 * 64
-
-    def level_hw(self, level):    # level 1..5 -> feature map size
-        h, w = self.padded
-        return h >> (level + 1), w >> (level + 1)
-
-    @property
-    def sensor(self):             # IDS parallel sensor (conf/test/things.yaml:18-20: divisor 32)
-        h, w = self.padded
-        return h // 32, w // 32
-
-
-CONFIGS = {
-    "things": StackConfig(),
-    "dsec": StackConfig(name="dsec", height=480, width=640, n_events=1_500_000, focal=1050.0 * 640 / 960),
-    "hd": StackConfig(name="hd", height=1080, width=1920, n_points=32768, n_events=4_000_000, focal=2100.0),
-    "tiny": StackConfig(name="tiny", height=128, width=192, n_points=8192, n_events=20_000),
-}
-
-
-def make_host_inputs(cfg, batch, first_sample=0, seed_base=1000, pin=False):
-    """Synthetic inputs for `batch` frame pairs (sample i is seeded seed_base + first_sample + i, so a shard can be
-    regenerated anywhere).  Everything lives in host memory (pinned on request): point clouds already in the
-    model's parallel-projection coordinates (models/utils.py:320-346), raw events, and the activations the hot
-    ops consume."""
-    hs, ws = cfg.sensor
-    hp, wp = cfg.padded
-    out = {"pcs": torch.empty(batch, 6, cfg.n_points), "feat2d": {}, "efeat2d": {}, "feat3d": {}, "flowfeat": {}}
-    if cfg.name == "dsec":
-        out["ev_x"] = torch.empty(batch, cfg.n_events)
-        out["ev_y"] = torch.empty(batch, cfg.n_events)
-        out["ev_p"] = torch.empty(batch, cfg.n_events)
-        out["ev_t"] = torch.empty(batch, cfg.n_events, dtype=torch.int64)
-    else:
-        out["events"] = torch.empty(batch, cfg.n_events, 4)
-    for lvl, c in zip(range(1, 6), LEVEL_CHANNELS):
-        h, w = cfg.level_hw(lvl)
-        n = PYRAMID_POINTS[lvl - 1]
-        out["feat2d"][lvl] = (torch.empty(batch, c, h, w), torch.empty(batch, c, h, w))   # image 1 / image 2 features
-        out["efeat2d"][lvl] = torch.empty(batch, c, h, w)             # event features
-        out["feat3d"][lvl] = (torch.empty(batch, c, n), torch.empty(batch, c, n))
-        out["flowfeat"][lvl] = (torch.empty(batch, 96, h, w), torch.empty(batch, 64, n))   # decoder features (pwc2d_core.py:119)
-    scale_w, scale_h = (ws - 1) / (wp - 1), (hs - 1) / (hp - 1)
-    for i in range(batch):
-        g = torch.Generator().manual_seed(seed_base + first_sample + i)
-        for half in range(2):     # FT3D-shaped cloud -> perspective projection -> IDS parallel coordinates
-            u = torch.rand(cfg.n_points, generator=g) * (cfg.width - 1)
-            v = torch.rand(cfg.n_points, generator=g) * (cfg.height - 1)
-            z = torch.rand(cfg.n_points, generator=g) * (cfg.max_depth - 2.0) + 2.0
-            out["pcs"][i, 3 * half + 0] = u * (wp - 1) / (cfg.width - 1) * scale_w - (ws - 1) / 2
-            out["pcs"][i, 3 * half + 1] = v * (hp - 1) / (cfg.height - 1) * scale_h - (hs - 1) / 2
-            out["pcs"][i, 3 * half + 2] = (cfg.focal * torch.log(z) + 1.0) * min(scale_w, scale_h)
-        n = cfg.n_events
-        if cfg.name == "dsec":
-            out["ev_x"][i] = torch.rand(n, generator=g) * (cfg.width - 1)
-            out["ev_y"][i] = torch.rand(n, generator=g) * (cfg.height - 1)
-            out["ev_t"][i] = torch.sort(torch.randint(0, 100_000, (n,), generator=g)).values
-            out["ev_p"][i] = torch.randint(0, 2, (n,), generator=g).float()
-        else:
-            ev = out["events"][i]
-            ev[:, 0] = torch.randint(0, cfg.width, (n,), generator=g).float()
-            ev[:, 1] = torch.randint(0, cfg.height, (n,), generator=g).float()
-            ev[:, 2] = torch.sort(torch.rand(n, generator=g)).values
-            ev[:, 3] = torch.randint(0, 2, (n,), generator=g).float() * 2 - 1
-        for lvl in range(1, 6):
-            for half in range(2):
-                out["feat2d"][lvl][half][i].normal_(generator=g)
-                out["feat3d"][lvl][half][i].normal_(generator=g)
-            out["efeat2d"][lvl][i].normal_(generator=g)
-            out["flowfeat"][lvl][0][i].normal_(generator=g)
-            out["flowfeat"][lvl][1][i].normal_(generator=g)
-    if pin:
-        out = _map_tensors(out, lambda t: t.pin_memory())
-    return out
-
-
-def _map_tensors(obj, fn):
-    if isinstance(obj, torch.Tensor):
-        return fn(obj)
-    if isinstance(obj, dict):
-        return {k: _map_tensors(v, fn) for k, v in obj.items()}
-    if isinstance(obj, (tuple, list)):
-        return type(obj)(_map_tensors(v, fn) for v in obj)
-    return obj
-
-
-def tensors_nbytes(obj):
-    total = 0
-
-    def add(t):
-        nonlocal total
-        total += t.numel() * t.element_size()
-        return t
-    _map_tensors(obj, add)
-    return total
-
-
-def to_device(host_inputs, device, non_blocking=True):
-    return _map_tensors(host_inputs, lambda t: t.to(device, non_blocking=non_blocking))
+from .workload import (CONFIGS, LEVEL_CHANNELS, PYRAMID_POINTS, StackConfig, _map_tensors, census_work,  # noqa: F401
+                       make_host_inputs, tensors_nbytes, to_device)
 
 
 class _OpTimer:
@@ -243,11 +123,11 @@ class CostVolumeStack:
         hs, ws = cfg.sensor
         pc1, pc2 = x["pcs"][:, :3].contiguous(), x["pcs"][:, 3:].contiguous()
         both = torch.cat([pc1, pc2], dim=0).transpose(1, 2).contiguous()                    # pwc3d_core.py:12-13
-        picked = T("fps", ops.furthest_point_sampling, both, max(PYRAMID_POINTS))
+        picked = T("fps", ops.furthest_point_sampling, both, max(cfg.pyramid))
         S["out"]["fps_idx"] = picked
         idx1, idx2 = picked[:B], picked[B:]
         xyzs1, xyzs2 = [pc1], [pc2]
-        for n in PYRAMID_POINTS:
+        for n in cfg.pyramid:
             xyzs1.append(T("gather_xyz", projection.batch_indexing_channel_first, pc1, idx1[:, :n]))
             xyzs2.append(T("gather_xyz", projection.batch_indexing_channel_first, pc2, idx2[:, :n]))
         S["xyzs1"], S["xyzs2"] = xyzs1, xyzs2
@@ -309,25 +189,25 @@ class CostVolumeStack:
         PR, GS = projection.project_feat_with_nn_corr, projection.grid_sample_wrapper
 
         def a():
-            p[0] = T("project_nn_corr", PR, xy1, f1_2d, f1_3d, nn1)                                        # :334
-            s[0] = T("grid_sample", GS, f1_2d, xy1)                                                        # :336
-            s[3] = T("grid_sample", GS, ef_2d, xy1)                                                        # :108
+            p[0] = T("project_nn_corr_L%d" % lvl, PR, xy1, f1_2d, f1_3d, nn1)                                        # :334
+            s[0] = T("grid_sample_L%d" % lvl, GS, f1_2d, xy1)                                                        # :336
+            s[3] = T("grid_sample_L%d" % lvl, GS, ef_2d, xy1)                                                        # :108
 
         def b():
-            p[1] = T("project_nn_corr", PR, xy2, f2_2d, f2_3d, nn2)                                        # :335
-            s[1] = T("grid_sample", GS, f2_2d, xy2)                                                        # :337
+            p[1] = T("project_nn_corr_L%d" % lvl, PR, xy2, f2_2d, f2_3d, nn2)                                        # :335
+            s[1] = T("grid_sample_L%d" % lvl, GS, f2_2d, xy2)                                                        # :337
 
         def c():
             flow3d_to_2d = xyz1[:, :2]                                                        # stand-in for the 2 flow channels
-            p[2] = T("project_nn_corr", PR, xy1, cost2d, torch.cat([cost3d, flow3d_to_2d], dim=1), nn1)    # :373 / :80
+            p[2] = T("project_nn_corr_L%d" % lvl, PR, xy1, cost2d, torch.cat([cost3d, flow3d_to_2d], dim=1), nn1)    # :373 / :80
             # :376 / :107 samples cat[cost volume, 2 flow channels] (83 ch); sampling is per channel, so the two parts are
             # sampled separately and only the small [B,83,N] result is concatenated (the 83-channel map is never built)
-            s[2] = torch.cat([T("grid_sample", GS, cost2d, xy1),
-                              T("grid_sample", GS, f1_2d[:, :2].contiguous(), xy1)], dim=1)
+            s[2] = torch.cat([T("grid_sample_L%d" % lvl, GS, cost2d, xy1),
+                              T("grid_sample_L%d" % lvl, GS, f1_2d[:, :2].contiguous(), xy1)], dim=1)
 
         def d():
-            p[3] = T("project_nn_corr", PR, xy1, dec_2d, dec_3d, nn1)                                      # :394
-            s[4] = T("grid_sample", GS, dec_2d, xy1)                                                       # :395
+            p[3] = T("project_nn_corr_L%d" % lvl, PR, xy1, dec_2d, dec_3d, nn1)                                      # :394
+            s[4] = T("grid_sample_L%d" % lvl, GS, dec_2d, xy1)                                                       # :395
         self._parallel(T, [a, b, c, d])
         S["out"]["proj"][lvl], S["out"]["sample"][lvl] = p, s
 
@@ -486,34 +366,3 @@ class GraphedStack:
                 wait(group)
             g.replay()
         return self.out
-
-
-# ---- algorithmic work of one frame pair, used by bench.py for the roofline arithmetic ----------------
-def census_work(cfg):
-    hs = {}
-    knn_pairs = 0
-    n_lvls = [cfg.n_points] + PYRAMID_POINTS
-    for lvl in range(5):
-        knn_pairs += 2 * n_lvls[lvl] * n_lvls[lvl + 1]
-    corr2d_bytes, gather_bytes, corr3d_flops = {}, 0, 0
-    for lvl, c in zip(range(1, 6), LEVEL_CHANNELS):
-        h, w = cfg.level_hw(lvl)
-        n = PYRAMID_POINTS[lvl - 1]
-        knn_pairs += 2 * n * h * w + 2 * n * n
-        if lvl < 5:
-            knn_pairs += PYRAMID_POINTS[lvl] * n + n * n
-        corr2d_bytes[lvl] = 4 * h * w * (2 * c + 81)
-        for cc in (c, c, 83, c, 96):
-            gather_bytes += 8 * n + 4 * cc * n + min(16 * cc * n, 4 * cc * h * w)
-        for c2, c3 in ((c, c), (c, c), (81, c + 2), (96, 64)):
-            gather_bytes += h * w * (8 + 4 * c2 + 4 * (c3 + 3)) + 4 * n * (c2 + c3 + 2)
-        corr3d_flops += 2 * n * cfg.k * ((2 * c + 3) * c + c * c) + 4 * n * cfg.k * (24 + 64 + 8 * c) + 4 * n * cfg.k * c
-    for i in range(5):
-        knn_pairs += n_lvls[i + 1] * n_lvls[i]
-    hs["knn_pairs"] = knn_pairs
-    hs["fps_updates"] = 2 * max(PYRAMID_POINTS) * cfg.n_points
-    hs["corr2d_bytes"] = corr2d_bytes
-    hs["gather_bytes"] = gather_bytes
-    hs["corr3d_flops"] = corr3d_flops
-    hs["event_voxel_bytes"] = 16 * cfg.n_events + 4 * 2 * cfg.event_bins * cfg.height * cfg.width
-    return hs

@@ -437,6 +437,35 @@ def test_project_nn_corr_golden_and_levels(golden):
         assert torch.equal(got[:, 3:].reshape(B, C3, -1), torch_ref.batch_indexing_channel_first(f3, nn))   # feat3d part is a pure gather
 
 
+def test_projection_sampler_serves_the_following_grid_sample_bit_exactly():
+    """project_feat_with_nn_corr(xy, f, ...) parks bilinear(f, xy); grid_sample_wrapper(f, xy) issued right after must return
+    exactly what the stand-alone sampling kernel returns, exactly once, and never after an in-place write to f or xy."""
+    from rpeflow_b200 import projection
+    gen = torch.Generator().manual_seed(21)
+    for (B, C2, C3, H, W, N) in [(2, 32, 32, 144, 240, 4096), (1, 81, 34, 72, 120, 2048), (2, 96, 64, 36, 60, 1024), (1, 7, 5, 9, 15, 31)]:
+        f2 = torch.randn(B, C2, H, W, generator=gen).to(DEV)
+        f3 = torch.randn(B, C3, N, generator=gen).to(DEV)
+        xy = (torch.rand(B, 2, N, generator=gen) * torch.tensor([W + 2.0, H + 2.0]).view(1, 2, 1) - 1.0).to(DEV)
+        projection.SAMPLE_MEMO.clear()
+        plain = b200.grid_sample_wrapper(f2, xy)                       # memo empty: the stand-alone kernel
+        h0 = projection.SAMPLE_MEMO.hits
+        b200.project_feat_with_nn_corr(xy, f2, f3)
+        served = b200.grid_sample_wrapper(f2, xy)
+        assert projection.SAMPLE_MEMO.hits == h0 + 1
+        assert torch.equal(served, plain)
+        again = b200.grid_sample_wrapper(f2, xy)                       # handed out once only
+        assert projection.SAMPLE_MEMO.hits == h0 + 1 and torch.equal(again, plain) and again.data_ptr() != served.data_ptr()
+        b200.project_feat_with_nn_corr(xy, f2, f3)
+        f2[:, 0].mul_(2.0)                                             # in-place write invalidates the parked samples
+        fresh = b200.grid_sample_wrapper(f2, xy)
+        assert projection.SAMPLE_MEMO.hits == h0 + 1
+        np.testing.assert_allclose(fresh.cpu().numpy(), spec.grid_sample_pts(f2.cpu().numpy(), xy.cpu().numpy()), rtol=1e-5, atol=1e-5)
+        b200.project_feat_with_nn_corr(xy, f2, f3)
+        other = xy.clone()
+        assert torch.equal(b200.grid_sample_wrapper(f2, other), fresh) and projection.SAMPLE_MEMO.hits == h0 + 1   # other tensor: no hit
+    projection.SAMPLE_MEMO.clear()
+
+
 # ------------------------------------------------------------------------------------------------- Correlation3D
 def _corr3d_inputs(B, C, N, k, seed):
     gen = torch.Generator().manual_seed(seed)

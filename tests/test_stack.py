@@ -66,7 +66,7 @@ def test_graph_replay_and_feeder_match_eager_run():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["dsec", "hd"])
+@pytest.mark.parametrize("name", ["dsec", "hd", "hd_scaled"])
 def test_other_baseline_configs_run_and_index_ops_stay_exact(name):
     """BASELINE.json configs[3] (DSEC-shaped: 640x480, tri-linear voxels) and configs[4] (1920x1080, 32768 points: FPS
     over a 4-CTA cluster, KNN over 32768 inputs): one frame pair through the whole stack; FPS and a sample of the KNN
@@ -81,10 +81,10 @@ def test_other_baseline_configs_run_and_index_ops_stay_exact(name):
     torch.cuda.synchronize()
     pcs = host["pcs"]
     both = torch.cat([pcs[:, :3], pcs[:, 3:]], 0).transpose(1, 2).contiguous().numpy()
-    np.testing.assert_array_equal(out["fps_idx"].cpu().numpy(), spec.fps(both, 4096))
+    np.testing.assert_array_equal(out["fps_idx"].cpu().numpy(), spec.fps(both, max(cfg.pyramid)))
     idx1 = out["fps_idx"][0].cpu()
     for lvl in (1, 4):
-        n = [4096, 2048, 1024, 512, 256][lvl - 1]
+        n = cfg.pyramid[lvl - 1]
         xyz = pcs[0, :3][:, idx1[:n]].t().contiguous().numpy()[None]
         want = spec.knn(xyz, xyz[:, :64], 16)
         np.testing.assert_array_equal(out["knn_self"][lvl][:, :64].cpu().numpy(), want)
@@ -93,4 +93,72 @@ def test_other_baseline_configs_run_and_index_ops_stay_exact(name):
             assert bool(torch.isfinite(t).all())
     n_ev = cfg.n_events
     total = float(out["event_voxel"].double().sum())
-    assert abs(total - n_ev) <= 1e-4 * n_ev if name == "hd" else total > 0     # integer-pixel voxels conserve the event count
+    assert abs(total - n_ev) <= 1e-4 * n_ev if name.startswith("hd") else total > 0     # integer-pixel voxels conserve the event count
+
+
+@pytest.mark.gpu
+def test_bench_batch_graph_replay_matches_the_oracle_on_first_and_last_sample():
+    """The shapes bench.py times: one CUDA-graph replay of the whole census over 74 frame pairs (persistent corr2d CTAs
+    walking thousands of tiles, 148-cloud FPS, multi-tile Correlation3D CTAs).  Samples 0 and 73 of every output are
+    compared with the CPU oracle: indices exactly, floats at the SURVEY §8a tolerances."""
+    import numpy as np
+    from oracle import spec
+    from rpeflow_b200 import pwc3d
+    dev = torch.device("cuda", 0)
+    cfg = CONFIGS["things"]
+    B = 74
+    host = make_host_inputs(cfg, B)
+    stack = CostVolumeStack(cfg, dev)
+    x = to_device(host, dev)
+    g = GraphedStack(stack, x, fused=True, with_checksum=False)
+    out = g.replay()
+    torch.cuda.synchronize()
+    hs, ws = cfg.sensor
+    both = torch.cat([host["pcs"][:, :3], host["pcs"][:, 3:]], 0).transpose(1, 2).contiguous().numpy()
+    for i in (0, B - 1):
+        sel = [i, B + i]
+        fps = out["fps_idx"][sel].cpu().numpy()
+        np.testing.assert_array_equal(fps, spec.fps(both[sel], max(cfg.pyramid)))
+        pc1, pc2 = host["pcs"][i, :3].numpy(), host["pcs"][i, 3:].numpy()
+        ev = host["events"][i].numpy()
+        want_vox, bad = spec.event_voxel_int(ev, cfg.event_bins, cfg.height, cfg.width, True)
+        vox = out["event_voxel"][i].cpu().numpy()
+        assert bad == 0 and np.all(np.abs(vox - want_vox) <= 1e-5 * np.maximum(1.0, want_vox))
+        for lvl in range(1, 6):
+            n = cfg.pyramid[lvl - 1]
+            h, w = cfg.level_hw(lvl)
+            xyz1 = np.ascontiguousarray(pc1[:, fps[0, :n]])[None]                    # [1,3,n]
+            xyz2 = np.ascontiguousarray(pc2[:, fps[1, :n]])[None]
+            x1n, x2n = np.ascontiguousarray(xyz1.transpose(0, 2, 1)), np.ascontiguousarray(xyz2.transpose(0, 2, 1))
+            knn11 = spec.knn(x1n, x1n, cfg.k)
+            np.testing.assert_array_equal(out["knn_self"][lvl][i:i + 1].cpu().numpy(), knn11)
+            knn12 = spec.knn(x2n, x1n, cfg.k)
+            f1_3d, f2_3d = host["feat3d"][lvl][0][i:i + 1].numpy(), host["feat3d"][lvl][1][i:i + 1].numpy()
+            wts = {k: v.cpu().numpy() for k, v in stack.corr3d[lvl].items()}
+            want = spec.corr3d_fwd(xyz1, f1_3d, xyz2, f2_3d, knn12, knn11, wts)
+            got = out["corr3d"][lvl][i:i + 1].cpu().numpy()
+            np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+            f1_2d, f2_2d = host["feat2d"][lvl][0][i:i + 1], host["feat2d"][lvl][1][i:i + 1]
+            want = spec.corr2d_fwd(f1_2d.permute(0, 2, 3, 1).contiguous().numpy(), f2_2d.permute(0, 2, 3, 1).contiguous().numpy(), 4)
+            cost2d = out["corr2d"][lvl][i:i + 1].cpu().numpy()
+            np.testing.assert_allclose(cost2d, want, rtol=1e-5, atol=1e-6)
+            # projections / samplers of this level: xy as the stack derives them, nn from the oracle's 2-D search
+            xy1_t = torch.from_numpy(pc1[:, fps[0, :n]])[None]
+            px = (xy1_t[:, 0:1] + (ws - 1) / 2) * ((w - 1) / (ws - 1))                # the stack's own torch arithmetic
+            py = (xy1_t[:, 1:2] + (hs - 1) / 2) * ((h - 1) / (hs - 1))
+            xy1 = torch.cat([px, py], 1).numpy()
+            ys, xs = np.meshgrid(np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
+            grid = np.stack([xs, ys], -1).reshape(1, h * w, 2)
+            nn1 = spec.knn(np.ascontiguousarray(xy1.transpose(0, 2, 1)), grid, 1)[..., 0]
+            p = out["proj"][lvl]
+            want = spec.project_nn_corr(xy1, f1_2d.numpy(), f1_3d, nn1)
+            np.testing.assert_allclose(p[0][i:i + 1].cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+            dec_2d, dec_3d = host["flowfeat"][lvl][0][i:i + 1].numpy(), host["flowfeat"][lvl][1][i:i + 1].numpy()
+            want = spec.project_nn_corr(xy1, dec_2d, dec_3d, nn1)
+            np.testing.assert_allclose(p[3][i:i + 1].cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+            s = out["sample"][lvl]
+            np.testing.assert_allclose(s[0][i:i + 1].cpu().numpy(), spec.grid_sample_pts(f1_2d.numpy(), xy1), rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(s[4][i:i + 1].cpu().numpy(), spec.grid_sample_pts(dec_2d, xy1), rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(s[2][i:i + 1, :81].cpu().numpy(), spec.grid_sample_pts(cost2d, xy1), rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(s[3][i:i + 1].cpu().numpy(), spec.grid_sample_pts(host["efeat2d"][lvl][i:i + 1].numpy(), xy1),
+                                       rtol=1e-5, atol=1e-5)
