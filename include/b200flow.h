@@ -157,8 +157,10 @@ B200_API int b200_grid_sample_pts(const float* feat_nchw, const float* xy, float
  *   xy [B,2,N]; feat2d [B,C2,H,W]; feat3d [B,C3,N]; nn [B,H*W] int64 -> out [B,C3+3,H,W]
  *   out[:,0:2] = xy[:,nn]-pixel ; out[:,2] = mean_c( bilinear(feat2d, xy[:,nn])[c] * feat2d[c,pixel] ) ;
  *   out[:,3:]  = feat3d[:,nn]
- *   scratch : >= B*N*C2 floats (holds feat2d sampled at the N points, point-major).
+ *   scratch : >= b200_project_nn_corr_scratch_floats(B, C2, C3, N) floats, 16-byte aligned (one point-major row per
+ *             point: feat2d sampled at the point, then the point's feat3d channels; each part padded to 4 floats).
  */
+B200_API int64_t b200_project_nn_corr_scratch_floats(int B, int C2, int C3, int N);
 B200_API int b200_project_nn_corr(const float* xy, const float* feat2d_nchw, const float* feat3d,
                          const int64_t* nn, float* out, float* scratch,
                          int B, int C2, int C3, int H, int W, int N, b200_stream_t stream);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200_gather_cl": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p]),
     "b200_grid_sample_pts": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "b200_project_nn_corr": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "b200_project_nn_corr_scratch_floats": (c_i64, [c_i, c_i, c_i, c_i]),
     "b200_project_nn_corr_sampled": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
     "b200_pointconv_scratch_floats": (c_i64, [c_i, c_i, c_i, c_i]),
     "b200_pointconv_fwd": (c_i, [c_p, c_p, c_p, c_p, ctypes.POINTER(PointConvWeights), c_p, c_p,

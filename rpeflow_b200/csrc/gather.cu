@@ -262,15 +262,21 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
     }
 }
 
-// a8, pass 1: S[b,n,c] = bilinear(feat2d[b,c], xy[b,:,n])  (point-major scratch).  Block = 16 points; compute: a warp
-// owns 4 of every 32 channels, lanes = 16 points x 2 tap sides (see half_taps); write: lane = channel (contiguous in S).
-// cf (optional): the same samples channel-first [B,C,N] — exactly what grid_sample_wrapper(feat2d, xy) returns
+// a8, pass 1: one point-major row per point, R[b,n,:] = [ S (C2p floats) | T (C3p floats) ] with
+//   S[c] = bilinear(feat2d[b,c], xy[b,:,n])   and   T[k] = feat3d[b,k,n]   (C2p, C3p = C2, C3 rounded up to 4),
+// so that pass 2 gathers both with 128-bit loads from ONE contiguous row per pixel (channel-first feat3d costs a
+// 32-byte sector per 4-byte element there: ncu showed that gather to be the largest consumer of L1 sector slots).
+// Block = 16 points; compute: a warp owns 4 of every 32 channels, lanes = 16 points x 2 tap sides (see half_taps);
+// write: lane = channel (contiguous in R).
+// cf (optional): the same samples channel-first [B,C2,N] — exactly what grid_sample_wrapper(feat2d, xy) returns
 // (same taps, same arithmetic as grid_sample_pts_kernel), written as 64-byte runs from the compute lanes.  The model asks
 // for that tensor right after this call in four of its five fuser pairs per level (RPEFlow_core.py:31+53, :80+107,
 // :134+157), so sampling once here saves a second pass over the whole feature map.
+__host__ __device__ __forceinline__ int round4(int c) { return (c + 3) & ~3; }
+
 __global__ void __launch_bounds__(256)
-sample_point_major_kernel(const float* __restrict__ feat, const float* __restrict__ xy, float* __restrict__ S,
-                          float* __restrict__ cf, int C, int H, int W, int N) {
+sample_point_major_kernel(const float* __restrict__ feat, const float* __restrict__ xy, const float* __restrict__ feat3d,
+                          float* __restrict__ R, float* __restrict__ cf, int C, int C3, int H, int W, int N) {
     __shared__ float tile[32][17];
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * 16;
@@ -278,6 +284,7 @@ sample_point_major_kernel(const float* __restrict__ feat, const float* __restric
     const int side = lane & 1, tp = lane >> 1;
     const int n = n0 + tp;
     const bool ok = n < N;
+    const int stride = round4(C) + round4(C3);
     Taps t = {-1, -1, -1, -1, 0.0f, 0.0f, 0.0f, 0.0f};
     if (ok) t = make_taps(__ldg(xy + ((size_t)b * 2 + 0) * N + n), __ldg(xy + ((size_t)b * 2 + 1) * N + n), H, W);
     const HalfTaps h = half_taps(t, side);
@@ -299,20 +306,38 @@ sample_point_major_kernel(const float* __restrict__ feat, const float* __restric
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int p = tc * 2 + u, c = c0 + lane;
-            if (n0 + p < N && c < C) S[((size_t)b * N + n0 + p) * C + c] = tile[lane][p];
+            if (n0 + p < N && c < C) R[((size_t)b * N + n0 + p) * stride + c] = tile[lane][p];
+        }
+    }
+    // T: feat3d[b, k, n0..n0+15] -> R[b, n, C2p + k].  Read: a half-warp = 16 consecutive points of one channel (64 bytes).
+    const int pt = lane & 15, ksub = lane >> 4;
+    const float* g = feat3d + (size_t)b * C3 * N;
+    float* Rt = R + round4(C);
+    for (int k0 = 0; k0 < C3; k0 += 32) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int kk = tc * 4 + u * 2 + ksub, k = k0 + kk;
+            tile[kk][pt] = (k < C3 && n0 + pt < N) ? __ldg(g + (size_t)k * N + n0 + pt) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int p = tc * 2 + u, k = k0 + lane;
+            if (n0 + p < N && k < C3) Rt[((size_t)b * N + n0 + p) * stride + k] = tile[lane][p];
         }
     }
 }
 
 // a8, pass 2: one thread per pixel.  blockIdx.z = 0: pixel offsets + channel-mean correlation; blockIdx.z >= 1: copies
-// a slab of 32 feat3d channels of the nearest point.  Batch items are visited last-to-first: pass 1 has just
-// streamed feat2d through L2 in ascending order, so the tail of the batch is still resident when this kernel starts.
+// a slab of 32 feat3d channels of the nearest point (128-bit loads from the point's row of R, coalesced streaming stores).
+// Batch items are visited last-to-first: pass 1 has just streamed feat2d through L2 in ascending order, so the tail of
+// the batch is still resident when this kernel starts.
 constexpr int PN_SLAB = 32;
 
 __global__ void __launch_bounds__(256)
-project_nn_corr_kernel(const float* __restrict__ xy, const float* __restrict__ feat2d, const float* __restrict__ feat3d,
-                       const int64_t* __restrict__ nn, const float* __restrict__ S, float* __restrict__ out,
-                       int C2, int C3, int H, int W, int N) {
+project_nn_corr_kernel(const float* __restrict__ xy, const float* __restrict__ feat2d, const int64_t* __restrict__ nn,
+                       const float* __restrict__ R, float* __restrict__ out, int C2, int C3, int H, int W, int N) {
     const int b = gridDim.y - 1 - blockIdx.y;
     const int HW = H * W;
     const int p = blockIdx.x * 256 + threadIdx.x;
@@ -321,56 +346,52 @@ project_nn_corr_kernel(const float* __restrict__ xy, const float* __restrict__ f
     if (j < 0) j += N;
     j = j < 0 ? 0 : (j >= N ? N - 1 : j);
     float* o = out + (size_t)b * (C3 + 3) * HW + p;
+    const int C2p = round4(C2), stride = C2p + round4(C3);
+    const float* row = R + ((size_t)b * N + j) * stride;                // 16-byte aligned: stride % 4 == 0
 
     if (blockIdx.z == 0) {
         const float px = (float)(p % W), py = (float)(p / W);          // mesh_grid: x in channel 0 (models/utils.py:177-179)
         o[0] = __ldg(xy + ((size_t)b * 2 + 0) * N + j) - px;
         o[(size_t)HW] = __ldg(xy + ((size_t)b * 2 + 1) * N + j) - py;
-        const float* s = S + ((size_t)b * N + j) * C2;
         const float* f = feat2d + (size_t)b * C2 * HW + p;
         float acc = 0.0f;
         int c = 0;
-        if ((C2 & 3) == 0) {
-            for (; c + 8 <= C2; c += 8) {                               // 8 plane reads in flight per thread
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + c));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + c + 4));
-                float v[8];
+        for (; c + 8 <= C2; c += 8) {                                   // 8 plane reads in flight per thread
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(row + c));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(row + c + 4));
+            float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldg(f + (size_t)(c + u) * HW);
-                acc += s0.x * v[0]; acc += s0.y * v[1]; acc += s0.z * v[2]; acc += s0.w * v[3];
-                acc += s1.x * v[4]; acc += s1.y * v[5]; acc += s1.z * v[6]; acc += s1.w * v[7];
-            }
-            for (; c < C2; c += 4) {
-                const float4 sv = __ldg(reinterpret_cast<const float4*>(s + c));
-                acc += sv.x * __ldg(f + (size_t)(c + 0) * HW);
-                acc += sv.y * __ldg(f + (size_t)(c + 1) * HW);
-                acc += sv.z * __ldg(f + (size_t)(c + 2) * HW);
-                acc += sv.w * __ldg(f + (size_t)(c + 3) * HW);
-            }
-        } else {                                                        // rows of S are not 16-byte aligned (C2 = 81: the cost volume)
-            for (; c + 8 <= C2; c += 8) {                               // same order of accumulation, 16 loads in flight
-                float sv[8], v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { sv[u] = __ldg(s + c + u); v[u] = __ldg(f + (size_t)(c + u) * HW); }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) acc += sv[u] * v[u];
-            }
-            for (; c < C2; ++c) acc += __ldg(s + c) * __ldg(f + (size_t)c * HW);
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(f + (size_t)(c + u) * HW);
+            acc += s0.x * v[0]; acc += s0.y * v[1]; acc += s0.z * v[2]; acc += s0.w * v[3];
+            acc += s1.x * v[4]; acc += s1.y * v[5]; acc += s1.z * v[6]; acc += s1.w * v[7];
         }
+        for (; c < C2; ++c) acc += __ldg(row + c) * __ldg(f + (size_t)c * HW);
         o[(size_t)2 * HW] = __fdiv_rn(acc, (float)C2);                  // torch.mean over channels
         return;
     }
     const int k0 = (blockIdx.z - 1) * PN_SLAB, k1 = min(k0 + PN_SLAB, C3);
-    const float* g = feat3d + (size_t)b * C3 * N + j;
+    const float* g = row + C2p;
     int k = k0;
-    for (; k + 8 <= k1; k += 8) {
-        float v[8];
+    for (; k + 16 <= k1; k += 16) {                                     // 4 row loads in flight, 16 plane stores
+        float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldg(g + (size_t)(k + u) * N);
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(g + k) + u);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) __stcs(o + (size_t)(3 + k + u) * HW, v[u]);
+        for (int u = 0; u < 4; ++u) {
+            __stcs(o + (size_t)(3 + k + 4 * u + 0) * HW, v[u].x);
+            __stcs(o + (size_t)(3 + k + 4 * u + 1) * HW, v[u].y);
+            __stcs(o + (size_t)(3 + k + 4 * u + 2) * HW, v[u].z);
+            __stcs(o + (size_t)(3 + k + 4 * u + 3) * HW, v[u].w);
+        }
     }
-    for (; k < k1; ++k) __stcs(o + (size_t)(3 + k) * HW, __ldg(g + (size_t)k * N));
+    for (; k + 4 <= k1; k += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g + k));
+        __stcs(o + (size_t)(3 + k + 0) * HW, v.x);
+        __stcs(o + (size_t)(3 + k + 1) * HW, v.y);
+        __stcs(o + (size_t)(3 + k + 2) * HW, v.z);
+        __stcs(o + (size_t)(3 + k + 3) * HW, v.w);
+    }
+    for (; k < k1; ++k) __stcs(o + (size_t)(3 + k) * HW, __ldg(g + k));
 }
 
 // f2: knn_interpolation (models/utils.py:140-156): out[b,c,q] = sum_s wn_s * feat[b,c,idx[b,q,s]], wn = normalised inverse
@@ -507,6 +528,11 @@ extern "C" int b200_convex_upsample(const float* flow, const float* mask, float*
     return B200_OK;
 }
 
+extern "C" int64_t b200_project_nn_corr_scratch_floats(int B, int C2, int C3, int N) {
+    if (B < 0 || C2 < 0 || C3 < 0 || N < 0) return 0;
+    return (int64_t)B * N * (b200::round4(C2) + b200::round4(C3));
+}
+
 extern "C" int b200_project_nn_corr(const float* xy, const float* feat2d, const float* feat3d, const int64_t* nn,
                                     float* out, float* scratch, int B, int C2, int C3, int H, int W, int N,
                                     b200_stream_t stream) {
@@ -523,10 +549,10 @@ extern "C" int b200_project_nn_corr_sampled(const float* xy, const float* feat2d
     B200_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "b200_project_nn_corr: scratch must be 16-byte aligned");
     if (B == 0) return B200_OK;
     cudaStream_t st = as_stream(stream);
-    sample_point_major_kernel<<<dim3(ceil_div(N, 16), B), 256, 0, st>>>(feat2d, xy, scratch, sampled_cf, C2, H, W, N);
+    sample_point_major_kernel<<<dim3(ceil_div(N, 16), B), 256, 0, st>>>(feat2d, xy, feat3d, scratch, sampled_cf, C2, C3, H, W, N);
     B200_LAUNCH_CHECK("b200_project_nn_corr(sample)");
     project_nn_corr_kernel<<<dim3(ceil_div((int64_t)H * W, 256), B, 1 + ceil_div(C3, PN_SLAB)), 256, 0, st>>>(
-        xy, feat2d, feat3d, nn, scratch, out, C2, C3, H, W, N);
+        xy, feat2d, nn, scratch, out, C2, C3, H, W, N);
     B200_LAUNCH_CHECK("b200_project_nn_corr");
     return B200_OK;
 }

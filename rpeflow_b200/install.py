@@ -232,7 +232,10 @@ _MODULES = ("models.utils", "models.RPEFlow_core", "models.pwc2d_core", "models.
             "models.losses3d", "models.RPEFlow", "models.csrc", "models.csrc.wrapper")
 
 
-def patch_python_ops(patch_events=True):
+def patch_python_ops(patch_events=True, only=None):
+    """only: optional set of names (function names as in models/utils.py / wrapper.py, or "Correlation3D", "PointConv",
+    "CorrFeatureFuser3D") — re-bind just those (ablations, staged roll-out); None = everything."""
+    want = (lambda n: True) if only is None else (lambda n: n in only)
     mutils = importlib.import_module("models.utils")
     wrapper = importlib.import_module("models.csrc.wrapper")
     ref = {n: getattr(mutils, n) for n in ("batch_indexing_channel_first", "batch_indexing_channel_last", "grid_sample_wrapper",
@@ -306,18 +309,21 @@ def patch_python_ops(patch_events=True):
         except Exception:
             continue
         for name, fn in replaced.items():
-            if hasattr(mod, name):
+            if hasattr(mod, name) and want(name):
                 _set(mod, name, fn)
-    pcm = importlib.import_module("models.pointconv")
-    _rebind_forward(pcm.PointConvDownSampling, _pointconv_down_forward)
-    _rebind_forward(pcm.PointConvNoSampling, _pointconv_nosample_forward)
-    core3 = importlib.import_module("models.pwc3d_core")
-    _rebind_forward(core3.Correlation3D, _corr3d_forward)
-    try:
-        core = importlib.import_module("models.RPEFlow_core")
-        _rebind_forward(core.CorrFeatureFuser3D, _corr_fuser3d_forward)
-    except Exception:                                    # the fuser is an optimisation, not a requirement
-        pass
+    if want("PointConv"):
+        pcm = importlib.import_module("models.pointconv")
+        _rebind_forward(pcm.PointConvDownSampling, _pointconv_down_forward)
+        _rebind_forward(pcm.PointConvNoSampling, _pointconv_nosample_forward)
+    if want("Correlation3D"):
+        core3 = importlib.import_module("models.pwc3d_core")
+        _rebind_forward(core3.Correlation3D, _corr3d_forward)
+    if want("CorrFeatureFuser3D"):
+        try:
+            core = importlib.import_module("models.RPEFlow_core")
+            _rebind_forward(core.CorrFeatureFuser3D, _corr_fuser3d_forward)
+        except Exception:                                # the fuser is an optimisation, not a requirement
+            pass
     if patch_events:
         try:
             _set(importlib.import_module("event_utils"), "eventsToVoxel", events.eventsToVoxel)
@@ -332,10 +338,11 @@ def patch_python_ops(patch_events=True):
             pass
 
 
-def install(patch_python=True, patch_events=False):
-    register_extension_shims()
+def install(patch_python=True, patch_events=False, only=None, extensions=True):
+    if extensions:
+        register_extension_shims()
     if patch_python:
-        patch_python_ops(patch_events=patch_events)
+        patch_python_ops(patch_events=patch_events, only=only)
 
 
 def uninstall():

@@ -189,7 +189,7 @@ def project_feat_with_nn_corr(xy, feat_2d, feat_3d, nn_indices=None, keep_sample
         assert tuple(nn_indices.shape) == (B, H * W)
     nn = _prep_idx(nn_indices, f2.device)
     out = torch.empty((B, C3 + 3, H, W), dtype=torch.float32, device=f2.device)
-    scratch = torch.empty((B, N, C2), dtype=torch.float32, device=f2.device)
+    scratch = torch.empty((max(1, lib.b200_project_nn_corr_scratch_floats(B, C2, C3, N)),), dtype=torch.float32, device=f2.device)
     sampled = torch.empty((B, C2, N), dtype=torch.float32, device=f2.device) if keep_samples else None
     with torch.cuda.device(f2.device):
         check(lib.b200_project_nn_corr_sampled(pts.data_ptr(), f2.data_ptr(), f3.data_ptr(), nn.data_ptr(), out.data_ptr(),
