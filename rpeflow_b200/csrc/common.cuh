@@ -111,7 +111,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ float leaky01(float v) { return v > 0.0f ? v : 0.1f * v; }
+// LeakyReLU(0.1): max(v, 0.1 v) selects the same value as (v > 0 ? v : 0.1 v) in two instructions instead of three
+__device__ __forceinline__ float leaky01(float v) { return fmaxf(v, 0.1f * v); }
 #endif
 
 }  // namespace b200

@@ -8,6 +8,8 @@ static inline int64_t align4(int64_t v) { return (v + 3) & ~int64_t(3); }
 
 struct Corr3dScratch {
     float *A1, *G2, *P, *W2T, *W1cT, *n1WcT, *n2WcT;
+    float *v2_W2img, *v2_wcimg;     // corr3d_v2.cu: W2 pre-split into its swizzled tile image; Wc / bias images of both weight nets
+    float *v2_W1img;                // ... and the two C x C halves of W1
     int64_t total;
 };
 static inline Corr3dScratch carve(float* base, int B, int Cout, int N1, int N2) {
@@ -21,6 +23,9 @@ static inline Corr3dScratch carve(float* base, int B, int Cout, int N1, int N2) 
     s.W1cT = take(3ll * Cout);
     s.n1WcT = take(8ll * Cout);
     s.n2WcT = take(8ll * Cout);
+    s.v2_W2img = take(2ll * Cout * Cout);
+    s.v2_wcimg = take(2ll * Cout * 32);
+    s.v2_W1img = take(4ll * Cout * Cout);
     s.total = off;
     return s;
 }
@@ -88,5 +93,11 @@ bool corr3d_stage1_tc_eligible(int Cout, int k, int precision);
 cudaError_t corr3d_stage1_tc(const float* xyz1, const float* xyz2, const int64_t* knn12, const Corr3dScratch& s,
                              const b200_corr3d_weights* w, int B, int Cout, int N1, int N2, int k, int precision,
                              cudaStream_t st);
+
+// corr3d_v2.cu: second-generation passes 2 + 3 (warp-specialised, every contraction on tcgen05); 3xTF32 only
+bool corr3d_v2_eligible(int C, int k, int precision);
+cudaError_t corr3d_v2_run(const float* xyz1, const float* feat1, const float* xyz2, const float* feat2, const int64_t* knn12,
+                          const int64_t* knn11, const Corr3dScratch& s, const b200_corr3d_weights* w, float* out, int B, int C, int N1,
+                          int N2, cudaStream_t st);
 
 }  // namespace b200
