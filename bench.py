@@ -527,7 +527,7 @@ def ref_cuda_column(cfg, stack, x, B, per_op, flush):
     h, w = cfg.level_hw(1)
     hs_, ws_ = cfg.sensor
     xy1 = torch.stack([(lv[1][:, 0] + (ws_ - 1) / 2) * ((w - 1) / (ws_ - 1)), (lv[1][:, 1] + (hs_ - 1) / 2) * ((h - 1) / (hs_ - 1))], 2).contiguous()
-    grid = stack.pixel_grid(B, h, w)
+    grid = stack.pixel_grid(B, h, w).transpose(1, 2).contiguous()
     cases = {"pyramid_k16 (N0->N1)": (cl[0], cl[1], 16), "self_k16 (L1)": (cl[1], cl[1], 16), "interp_k3 (L2->L1)": (cl[2], cl[1], 3),
              "2d_k1 (L1 points -> pixel grid)": (xy1, grid, 1), "self_k32 (L1, configs[2])": (cl[1], cl[1], 32)}
     knn = {}
@@ -745,7 +745,7 @@ def main():
         n = cfg.pyramid[lvl - 1]
         dec_2d, dec_3d = x["flowfeat"][lvl]
         xy = torch.rand(B, 2, n, device=dev) * torch.tensor([w - 1.0, h - 1.0], device=dev).view(1, 2, 1)
-        nn = _ops.k_nearest_neighbor(xy, stack.pixel_grid(B, h, w).transpose(1, 2).contiguous(), 1)[..., 0]
+        nn = _ops.k_nearest_neighbor(xy, stack.pixel_grid(B, h, w), 1)[..., 0]
         ms = time_isolated(lambda: projection.project_feat_with_nn_corr(xy, dec_2d, dec_3d, nn), flush)
         nb = project_bytes(96, 64, n, h, w) * B
         iso = {"call": f"project_feat_with_nn_corr(C2=96, C3=64) at level {lvl}, batch {B} (2 launches)", "launch_ms": round(ms, 4),

@@ -128,6 +128,11 @@ B200_API int b200_knn_grid(const float* input_xyz, const float* query_xyz, int64
                   void* scratch, int64_t scratch_bytes,
                   int B, int M, int Q, int D, int k, b200_stream_t stream);
 
+/* The same search on CHANNEL-FIRST clouds: input_xyz [B,D,M], query_xyz [B,D,Q] — the layout every model call site
+ * passes (models/csrc/wrapper.py:119-122 transposes + copies them per call; this entry reads them as they are). */
+B200_API int b200_knn_grid_cf(const float* input_xyz, const float* query_xyz, int64_t* idx, void* scratch,
+                              int64_t scratch_bytes, int B, int M, int Q, int D, int k, b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * a6  batched index gathers.  Elements are 4 bytes wide and moved bit-exactly (fp32 or int32 data).
  * Replaces: models/utils.py:119-137 (batch_indexing_channel_first) and :101-116 (.._channel_last).

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200flow.so")
+LIB_PATH = os.environ.get("B200FLOW_LIB") or os.path.join(_HERE, "libb200flow.so")     # the override is for kernel A/B builds
 ABI_VERSION = 7
 
 c_i, c_i64, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
@@ -43,6 +43,7 @@ SIGNATURES = {
     "b200_knn": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "b200_knn_scratch_bytes": (c_i64, [c_i, c_i, c_i, c_i, c_i]),
     "b200_knn_grid": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "b200_knn_grid_cf": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i, c_p]),
     "b200_gather_cf": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p]),
     "b200_gather_cl": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p]),
     "b200_grid_sample_pts": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
@@ -81,7 +82,7 @@ def _load():
 
 lib = _load()
 LAUNCHES = 0          # kernels of this library launched by this process (bench.py reports it as gpu_launches)
-KERNELS_PER_CALL = {"b200_knn_grid": 3, "b200_pointconv_fwd": 2, "b200_corr2d_bwd": 2, "b200_project_nn_corr": 2, "b200_corr3d_fwd": 5, "b200_event_voxel_trilinear": 3}
+KERNELS_PER_CALL = {"b200_knn_grid": 3, "b200_knn_grid_cf": 3, "b200_pointconv_fwd": 2, "b200_corr2d_bwd": 2, "b200_project_nn_corr": 2, "b200_corr3d_fwd": 5, "b200_event_voxel_trilinear": 3}
 
 
 class B200Error(RuntimeError):

@@ -30,6 +30,15 @@
 namespace b200 {
 
 constexpr int V2_ROWS = 128, V2_KB = 32, V2_K = 16;
+#ifndef V2_GROUP
+#define V2_GROUP 4
+#endif
+#ifndef V2_MINB
+#define V2_MINB 4
+#endif
+#ifndef V2_PREJ
+#define V2_PREJ 0
+#endif
 constexpr int V2_TILE = V2_ROWS * 128;                  // one 128-row operand tile: 16 KB
 
 // ---- mbarrier / bulk-copy helpers --------------------------------------------------------------------------------
@@ -185,7 +194,7 @@ __device__ __forceinline__ void v2_hidden_full(const float* s_wn, float dx, floa
 // DEPTH = stages of the operand ring / HID buffers (2 also double-buffers the accumulators when 4*C <= 512 columns).
 // =====================================================================================================================
 template <int NW, int DEPTH>
-__global__ void __launch_bounds__(NW * 32 + 32, NW == 4 ? 4 : 1)
+__global__ void __launch_bounds__(NW * 32 + 32, NW == 4 ? V2_MINB : 1)
 corr3d_v2_stage1_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2, const int64_t* __restrict__ knn12,
                         const float* __restrict__ A1, const float* __restrict__ G2, const float* __restrict__ W2img,
                         const float* __restrict__ wcimg, const float* __restrict__ W1cT, const float* __restrict__ Wa,
@@ -315,7 +324,7 @@ corr3d_v2_stage1_kernel(const float* __restrict__ xyz1, const float* __restrict_
             jpre = __ldg(knn12 + ((size_t)b * N1 + i) * V2_K + (row & 15));
             jpre_item = item;
         };
-        constexpr int STEPS = 1024 / NWT, GROUP = 4;
+        constexpr int STEPS = 1024 / NWT, GROUP = V2_GROUP;
         auto convert = [&](const float4& a, const float4& g, int r, int q, const float4& wx, const float4& wy, const float4& wz,
                            uint8_t* a_hi, uint8_t* a_lo) {
             const float4 d = s_d[r];
@@ -342,7 +351,7 @@ corr3d_v2_stage1_kernel(const float* __restrict__ xyz1, const float* __restrict_
                             z2 = __ldg(xyz2 + ((size_t)b * 3 + 2) * N2 + j);
                 const float x1 = __ldg(xyz1 + ((size_t)b * 3 + 0) * N1 + i), y1 = __ldg(xyz1 + ((size_t)b * 3 + 1) * N1 + i),
                             z1 = __ldg(xyz1 + ((size_t)b * 3 + 2) * N1 + i);
-                if (DEEP && item + gridDim.x < items) fetch_j(item + gridDim.x);   // in flight until the next produce()
+                if ((DEEP || V2_PREJ) && item + gridDim.x < items) fetch_j(item + gridDim.x);   // in flight until the next produce()
                 const float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
                 uint8_t* hid = gbase + HID_OFF(lt % DEPTH);
                 if (NW == 8) {                              // two threads per row: `half` selects four of the eight outputs

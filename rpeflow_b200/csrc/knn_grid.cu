@@ -64,8 +64,10 @@ __device__ __forceinline__ int kg_cell_index(const KnnGridParams& p, float x, fl
 // ---- build: bounding box + cell geometry (make_params) -> histogram -> scan -> scatter ---------------------------
 template <int D>
 __global__ void __launch_bounds__(KG_BUILD_THREADS)
-knn_grid_build_kernel(const float* __restrict__ pts, int M, int ctarget, int make_params, KnnGridParams* __restrict__ params,
-                      int* __restrict__ cell_start, float4* __restrict__ sorted) {
+knn_grid_build_kernel(const float* __restrict__ pts, int M, int sp, int sd, int ctarget, int make_params,
+                      KnnGridParams* __restrict__ params, int* __restrict__ cell_start, float4* __restrict__ sorted) {
+    // coordinate d of point i is pts[i * sp + d * sd]: (sp, sd) = (D, 1) for point-major [M,D] clouds (the extension entry,
+    // k_nearest_neighbor.cpp:6) and (1, M) for the channel-first [D,M] clouds every model call site passes (wrapper.py:119)
     extern __shared__ int s_hist[];                      // [cells + 1]
     __shared__ float s_red[2 * 3][32];
     __shared__ int s_warp_tot[32];
@@ -78,7 +80,7 @@ knn_grid_build_kernel(const float* __restrict__ pts, int M, int ctarget, int mak
         for (int i = tid; i < M; i += KG_BUILD_THREADS) {
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                const float v = __ldg(pts + (size_t)i * D + d);
+                const float v = __ldg(pts + (size_t)i * sp + (size_t)d * sd);
                 mn[d] = fminf(mn[d], v);                 // fminf/fmaxf drop NaNs
                 mx[d] = fmaxf(mx[d], v);
             }
@@ -142,8 +144,8 @@ knn_grid_build_kernel(const float* __restrict__ pts, int M, int ctarget, int mak
     for (int c = tid; c <= cells; c += KG_BUILD_THREADS) s_hist[c] = 0;
     __syncthreads();
     for (int i = tid; i < M; i += KG_BUILD_THREADS) {
-        const float x = __ldg(pts + (size_t)i * D), y = __ldg(pts + (size_t)i * D + 1);
-        const float z = D == 3 ? __ldg(pts + (size_t)i * D + 2) : 0.0f;
+        const float x = __ldg(pts + (size_t)i * sp), y = __ldg(pts + (size_t)i * sp + sd);
+        const float z = D == 3 ? __ldg(pts + (size_t)i * sp + 2 * (size_t)sd) : 0.0f;
         atomicAdd(&s_hist[kg_cell_index<D>(p, x, y, z)], 1);
     }
     __syncthreads();
@@ -186,8 +188,8 @@ knn_grid_build_kernel(const float* __restrict__ pts, int M, int ctarget, int mak
     __syncthreads();
     float4* out = sorted + (size_t)b * M;
     for (int i = tid; i < M; i += KG_BUILD_THREADS) {    // s_hist now serves as the per-cell write cursor
-        const float x = __ldg(pts + (size_t)i * D), y = __ldg(pts + (size_t)i * D + 1);
-        const float z = D == 3 ? __ldg(pts + (size_t)i * D + 2) : 0.0f;
+        const float x = __ldg(pts + (size_t)i * sp), y = __ldg(pts + (size_t)i * sp + sd);
+        const float z = D == 3 ? __ldg(pts + (size_t)i * sp + 2 * (size_t)sd) : 0.0f;
         const int pos = atomicAdd(&s_hist[kg_cell_index<D>(p, x, y, z)], 1);
         out[pos] = make_float4(x, y, z, __int_as_float(i));
     }
@@ -257,7 +259,7 @@ struct KgQuery {
 
 template <int D>
 __device__ __forceinline__ KgQuery kg_load_query(const KnnGridParams& p, const float4* __restrict__ sorted_q,
-                                                 const float* __restrict__ raw_q, int b, int t, int Q) {
+                                                 const float* __restrict__ raw_q, int qsp, int qsd, int b, int t, int Q) {
     KgQuery q;
     q.live = t < Q;
     q.qx = q.qy = q.qz = 0.0f;
@@ -267,9 +269,9 @@ __device__ __forceinline__ KgQuery kg_load_query(const KnnGridParams& p, const f
             const float4 v = __ldg(sorted_q + (size_t)b * Q + t);
             q.qx = v.x; q.qy = v.y; q.qz = v.z; q.orig = __float_as_int(v.w);
         } else {
-            const float* v = raw_q + ((size_t)b * Q + t) * D;
-            q.qx = __ldg(v); q.qy = __ldg(v + 1);
-            if (D == 3) q.qz = __ldg(v + 2);
+            const float* v = raw_q + (size_t)b * Q * D + (size_t)t * qsp;
+            q.qx = __ldg(v); q.qy = __ldg(v + qsd);
+            if (D == 3) q.qz = __ldg(v + 2 * (size_t)qsd);
         }
     }
     q.cx = kg_cell(q.qx, p.lo[0], p.inv_h, p.G[0]);
@@ -315,12 +317,12 @@ template <int D, int KMAX>
 __global__ void __launch_bounds__(KG_QUERY_THREADS)
 knn_grid_query_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ cell_start,
                       const KnnGridParams* __restrict__ params, const float4* __restrict__ sorted_q,
-                      const float* __restrict__ raw_q, int64_t* __restrict__ out, int M, int Q, int k) {
+                      const float* __restrict__ raw_q, int qsp, int qsd, int64_t* __restrict__ out, int M, int Q, int k) {
     __shared__ KnnGridParams s_p;
     const int b = blockIdx.y, t = blockIdx.x * KG_QUERY_THREADS + threadIdx.x;
     if (threadIdx.x == 0) s_p = params[b];
     __syncthreads();
-    const KgQuery q = kg_load_query<D>(s_p, sorted_q, raw_q, b, t, Q);
+    const KgQuery q = kg_load_query<D>(s_p, sorted_q, raw_q, qsp, qsd, b, t, Q);
     if (!q.live) return;
     sorted_pts += (size_t)b * M;
     const int* cs = cell_start + (size_t)b * (KG_CELLS_MAX + 1);
@@ -373,13 +375,13 @@ template <int D, int KMAX>
 __global__ void __launch_bounds__(KG_QUERY_THREADS)
 knn_grid_query_batched_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ cell_start,
                               const KnnGridParams* __restrict__ params, const float4* __restrict__ sorted_q,
-                              const float* __restrict__ raw_q, int64_t* __restrict__ out, int M, int Q, int k) {
+                              const float* __restrict__ raw_q, int qsp, int qsd, int64_t* __restrict__ out, int M, int Q, int k) {
     __shared__ u64 s_batch[KMAX][KG_QUERY_THREADS];
     __shared__ KnnGridParams s_p;
     const int b = blockIdx.y, t = blockIdx.x * KG_QUERY_THREADS + threadIdx.x;
     if (threadIdx.x == 0) s_p = params[b];
     __syncthreads();
-    const KgQuery q = kg_load_query<D>(s_p, sorted_q, raw_q, b, t, Q);   // dead lanes follow the warp with no candidates
+    const KgQuery q = kg_load_query<D>(s_p, sorted_q, raw_q, qsp, qsd, b, t, Q);   // dead lanes follow the warp with no candidates
     sorted_pts += (size_t)b * M;
     const int* cs = cell_start + (size_t)b * (KG_CELLS_MAX + 1);
     const int Gx = s_p.G[0], Gy = s_p.G[1], Gz = s_p.G[2];
@@ -485,35 +487,38 @@ static KnnGridScratch kg_carve(void* base, int B, int M, int Q, int D) {
 }
 
 template <int D, int KMAX>
-static void kg_launch_query(const KnnGridScratch& s, const float* query, int64_t* idx, int B, int M, int Q, int k, cudaStream_t st) {
+static void kg_launch_query(const KnnGridScratch& s, const float* query, int qsp, int qsd, int64_t* idx, int B, int M, int Q, int k,
+                            cudaStream_t st) {
     dim3 grid(ceil_div(Q, KG_QUERY_THREADS), B);
     if constexpr (KMAX >= 16)
         knn_grid_query_batched_kernel<D, KMAX><<<grid, KG_QUERY_THREADS, 0, st>>>(s.sorted_pts, s.cell_start, s.params, s.sorted_q,
-                                                                                  query, idx, M, Q, k);
+                                                                                  query, qsp, qsd, idx, M, Q, k);
     else
         knn_grid_query_kernel<D, KMAX><<<grid, KG_QUERY_THREADS, 0, st>>>(s.sorted_pts, s.cell_start, s.params, s.sorted_q, query,
-                                                                          idx, M, Q, k);
+                                                                          qsp, qsd, idx, M, Q, k);
 }
 
 template <int D>
 static cudaError_t kg_run(const float* input, const float* query, int64_t* idx, const KnnGridScratch& s, int B, int M, int Q,
-                          int k, cudaStream_t st) {
+                          int k, bool channel_first, cudaStream_t st) {
+    const int isp = channel_first ? 1 : D, isd = channel_first ? M : 1;      // strides of the input cloud
+    const int qsp = channel_first ? 1 : D, qsd = channel_first ? Q : 1;      // ... and of the queries
     const size_t smem = (size_t)(KG_CELLS_MAX + 1) * sizeof(int);
     cudaError_t e = cudaFuncSetAttribute(knn_grid_build_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int ctarget = k / 2 < 2 ? 2 : (k / 2 > 16 ? 16 : k / 2);
-    knn_grid_build_kernel<D><<<B, KG_BUILD_THREADS, smem, st>>>(input, M, ctarget, 1, s.params, s.cell_start, s.sorted_pts);
+    knn_grid_build_kernel<D><<<B, KG_BUILD_THREADS, smem, st>>>(input, M, isp, isd, ctarget, 1, s.params, s.cell_start, s.sorted_pts);
     KnnGridScratch q = s;
     if (s.sorted_q) {
         if (query == input && Q == M) q.sorted_q = s.sorted_pts;    // self search: the inputs' cell order is the queries'
         else                                                         // queries into the inputs' cells (no cell table needed)
-            knn_grid_build_kernel<D><<<B, KG_BUILD_THREADS, smem, st>>>(query, Q, ctarget, 0, s.params, nullptr, s.sorted_q);
+            knn_grid_build_kernel<D><<<B, KG_BUILD_THREADS, smem, st>>>(query, Q, qsp, qsd, ctarget, 0, s.params, nullptr, s.sorted_q);
     }
-    if (k == 1) kg_launch_query<D, 1>(q, query, idx, B, M, Q, k, st);
-    else if (k <= 4) kg_launch_query<D, 4>(q, query, idx, B, M, Q, k, st);
-    else if (k <= 8) kg_launch_query<D, 8>(q, query, idx, B, M, Q, k, st);
-    else if (k <= 16) kg_launch_query<D, 16>(q, query, idx, B, M, Q, k, st);
-    else kg_launch_query<D, 32>(q, query, idx, B, M, Q, k, st);
+    if (k == 1) kg_launch_query<D, 1>(q, query, qsp, qsd, idx, B, M, Q, k, st);
+    else if (k <= 4) kg_launch_query<D, 4>(q, query, qsp, qsd, idx, B, M, Q, k, st);
+    else if (k <= 8) kg_launch_query<D, 8>(q, query, qsp, qsd, idx, B, M, Q, k, st);
+    else if (k <= 16) kg_launch_query<D, 16>(q, query, qsp, qsd, idx, B, M, Q, k, st);
+    else kg_launch_query<D, 32>(q, query, qsp, qsd, idx, B, M, Q, k, st);
     return cudaGetLastError();
 }
 
@@ -525,8 +530,21 @@ extern "C" int64_t b200_knn_scratch_bytes(int B, int M, int Q, int D, int k) {
     return b200::kg_carve(nullptr, B, M, Q, D).total;
 }
 
+static int knn_grid_entry(const float* input_xyz, const float* query_xyz, int64_t* idx, void* scratch, int64_t scratch_bytes, int B,
+                          int M, int Q, int D, int k, bool channel_first, b200_stream_t stream);
+
 extern "C" int b200_knn_grid(const float* input_xyz, const float* query_xyz, int64_t* idx, void* scratch,
                              int64_t scratch_bytes, int B, int M, int Q, int D, int k, b200_stream_t stream) {
+    return knn_grid_entry(input_xyz, query_xyz, idx, scratch, scratch_bytes, B, M, Q, D, k, false, stream);
+}
+
+extern "C" int b200_knn_grid_cf(const float* input_xyz, const float* query_xyz, int64_t* idx, void* scratch,
+                                int64_t scratch_bytes, int B, int M, int Q, int D, int k, b200_stream_t stream) {
+    return knn_grid_entry(input_xyz, query_xyz, idx, scratch, scratch_bytes, B, M, Q, D, k, true, stream);
+}
+
+static int knn_grid_entry(const float* input_xyz, const float* query_xyz, int64_t* idx, void* scratch, int64_t scratch_bytes, int B,
+                          int M, int Q, int D, int k, bool channel_first, b200_stream_t stream) {
     using namespace b200;
     B200_REQUIRE((B == 0 || Q == 0) || (input_xyz && query_xyz && idx && scratch), "b200_knn_grid: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(D == 2 || D == 3, "b200_knn_grid: D must be 2 or 3 (got %d)", D);
@@ -538,8 +556,8 @@ extern "C" int b200_knn_grid(const float* input_xyz, const float* query_xyz, int
     B200_REQUIRE(scratch_bytes >= s.total, "b200_knn_grid: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes,
                  (long long)s.total);
     if (B == 0 || Q == 0) return B200_OK;
-    const cudaError_t e = D == 2 ? kg_run<2>(input_xyz, query_xyz, idx, s, B, M, Q, k, as_stream(stream))
-                                 : kg_run<3>(input_xyz, query_xyz, idx, s, B, M, Q, k, as_stream(stream));
+    const cudaError_t e = D == 2 ? kg_run<2>(input_xyz, query_xyz, idx, s, B, M, Q, k, channel_first, as_stream(stream))
+                                 : kg_run<3>(input_xyz, query_xyz, idx, s, B, M, Q, k, channel_first, as_stream(stream));
     if (e != cudaSuccess) return cuda_fail(e, "b200_knn_grid");
     return B200_OK;
 }

@@ -92,18 +92,26 @@ def _knn_check(input_xyz, query_xyz):
              and input_xyz.shape[2] == query_xyz.shape[2], "input_xyz/query_xyz must be [B,M,D]/[B,Q,D]")
 
 
-def _k_nearest_neighbor_cuda(input_xyz, query_xyz, k):
+def _k_nearest_neighbor_cuda(input_xyz, query_xyz, k, channel_first=False):
     """input [B,M,D], query [B,Q,D] -> [B,Q,k] int64 (replaces k_nearest_neighbor.cpp:6-24).  Exact search over a
-    cell grid (b200_knn_grid); bit-identical to the brute-force scan of knn_bruteforce()."""
-    _knn_check(input_xyz, query_xyz)
-    B, M, D = input_xyz.shape
-    Q = query_xyz.shape[1]
+    cell grid (b200_knn_grid); bit-identical to the brute-force scan of knn_bruteforce().
+    channel_first=True: input [B,D,M], query [B,D,Q] read as they are (b200_knn_grid_cf)."""
+    _knn_check(input_xyz, query_xyz) if not channel_first else (_cuda_f32(input_xyz, "input_xyz"), _cuda_f32(query_xyz, "query_xyz"))
+    if channel_first:
+        _require(input_xyz.dim() == 3 and query_xyz.dim() == 3 and input_xyz.shape[:2] == query_xyz.shape[:2],
+                 "input_xyz/query_xyz must be [B,D,M]/[B,D,Q]")
+        B, D, M = input_xyz.shape
+        Q = query_xyz.shape[2]
+    else:
+        B, M, D = input_xyz.shape
+        Q = query_xyz.shape[1]
     out = torch.empty((B, Q, int(k)), dtype=torch.int64, device=query_xyz.device)
     nbytes = lib.b200_knn_scratch_bytes(B, M, Q, D, int(k))
     scratch = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=query_xyz.device)     # torch blocks are 512-B aligned
+    fn, name = (lib.b200_knn_grid_cf, "b200_knn_grid_cf") if channel_first else (lib.b200_knn_grid, "b200_knn_grid")
     with torch.cuda.device(query_xyz.device):
-        check(lib.b200_knn_grid(input_xyz.data_ptr(), query_xyz.data_ptr(), out.data_ptr(), scratch.data_ptr(), nbytes,
-                                B, M, Q, D, int(k), _stream(query_xyz)), "b200_knn_grid")
+        check(fn(input_xyz.data_ptr(), query_xyz.data_ptr(), out.data_ptr(), scratch.data_ptr(), nbytes,
+                 B, M, Q, D, int(k), _stream(query_xyz)), name)
     return out
 
 
@@ -223,10 +231,9 @@ def furthest_point_sampling(xyz, n_samples, cpp_impl=True):
 def k_nearest_neighbor(input_xyz, query_xyz, k, cpp_impl=True):
     """[B,N,D] or [B,D,N] (D<=3, sniffed like wrapper.py:119-122) -> [B,Q,k] int64 (wrapper.py:106-127)."""
     _no_fallback("k_nearest_neighbor", input_xyz, query_xyz)
-    if input_xyz.shape[1] <= 3:
+    if input_xyz.shape[1] <= 3:                          # channel-first: read in place, no transpose().contiguous() passes
         assert query_xyz.shape[1] == input_xyz.shape[1]
-        input_xyz = input_xyz.transpose(1, 2).contiguous()
-        query_xyz = query_xyz.transpose(1, 2).contiguous()
+        return _k_nearest_neighbor_cuda(input_xyz.contiguous(), query_xyz.contiguous(), k, channel_first=True)
     return _k_nearest_neighbor_cuda(input_xyz.contiguous(), query_xyz.contiguous(), k)
 
 

@@ -70,8 +70,8 @@ class CostVolumeStack:
         if key not in self._grids:                    # mesh_grid cache of the reference (models/utils.py:172-183)
             ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=self.device),
                                     torch.arange(w, dtype=torch.float32, device=self.device), indexing="ij")
-            self._grids[key] = torch.stack([xs, ys], 0).reshape(1, 2, h * w).expand(batch, 2, h * w).transpose(1, 2).contiguous()
-        return self._grids[key]                       # [B,HW,2] channel-last: what wrapper.py:119-122 produces per call
+            self._grids[key] = torch.stack([xs, ys], 0).reshape(1, 2, h * w).expand(batch, 2, h * w).contiguous()
+        return self._grids[key]                       # [B,2,HW] channel-first, as RPEFlow_core.py:326-327 passes it
 
     def voxelise(self, x):
         cfg = self.cfg
@@ -145,8 +145,8 @@ class CostVolumeStack:
                 return torch.cat([px, py], dim=1)
             xy1, xy2 = to_pixels(xyzs1[lvl]), to_pixels(xyzs2[lvl])
             grid = self.pixel_grid(B, h, w)
-            nn1 = T("knn_2d_k1", ops.k_nearest_neighbor, xy1.transpose(1, 2).contiguous(), grid, 1)      # :329
-            nn2 = T("knn_2d_k1", ops.k_nearest_neighbor, xy2.transpose(1, 2).contiguous(), grid, 1)      # :330
+            nn1 = T("knn_2d_k1", ops.k_nearest_neighbor, xy1, grid, 1)                                   # :329
+            nn2 = T("knn_2d_k1", ops.k_nearest_neighbor, xy2, grid, 1)                                   # :330
             S[lvl] = {"xy1": xy1, "xy2": xy2, "nn1": nn1[..., 0], "nn2": nn2[..., 0]}
 
         def cost3d(lvl):
