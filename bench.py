@@ -556,6 +556,41 @@ def ref_cuda_column(cfg, stack, x, B, per_op, flush):
     return out
 
 
+@torch.no_grad()
+def pointconv_leg(cfg, x, B, dev):
+    """The 20 PointConv bodies of one forward at the bench batch: 10 PointConvDownSampling of the feature
+    pyramid (pwc3d_core.py:44-57; C = 32..192, N_l -> N_l+1, two clouds) and 10 PointConvNoSampling of FlowEstimator3D
+    (pwc3d_core.py:118-143; 195 -> 128 -> 128 at every level).  Outside the census (and `value`), reported beside it."""
+    from rpeflow_b200 import ops, pointconv, projection
+    torch.manual_seed(0)
+    pcs = [x["pcs"][:, :3].contiguous(), x["pcs"][:, 3:].contiguous()]
+    both = torch.cat(pcs, 0).transpose(1, 2).contiguous()
+    picked = ops.furthest_point_sampling(both, max(cfg.pyramid))
+    pyr = [[pc] + [projection.batch_indexing_channel_first(pc, picked[i * B:(i + 1) * B, :n]) for n in cfg.pyramid] for i, pc in enumerate(pcs)]
+    chans = [32, 64, 96, 128, 192]
+    down = [pointconv.PointConvDownSampling(c, c).to(dev).eval() for c in chans]
+    est1, est2 = pointconv.PointConvNoSampling(195, 128).to(dev).eval(), pointconv.PointConvNoSampling(128, 128).to(dev).eval()
+    feats = [[torch.randn(B, chans[l], pyr[i][l].shape[2], device=dev) for l in range(5)] for i in range(2)]
+    efeat = [torch.randn(B, 195, n, device=dev) for n in cfg.pyramid]
+    knn = [ops.k_nearest_neighbor(pyr[0][l + 1], pyr[0][l + 1], 16) for l in range(5)]
+
+    def run():
+        for i in range(2):
+            for l in range(5):
+                down[l](pyr[i][l], feats[i][l], pyr[i][l + 1])
+        for l in range(5):
+            est2(pyr[0][l + 1], est1(pyr[0][l + 1], efeat[l], knn[l]), knn[l])
+    run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for _ in range(3):
+        a.record(); run(); b.record(); b.synchronize()
+        ms.append(a.elapsed_time(b))
+    return {"ms_per_step": round(min(ms), 4), "calls": 20, "includes": "the 10 pyramid KNN searches inside PointConvDownSampling",
+            "note": "not part of the census / `value` (SURVEY §8d fixes the census); reported for visibility"}
+
+
 def model_leg(args, dev):
     """model_e2e: the UNMODIFIED reference model (RPEFlow.forward, eval_withocc.py:54-63) at 960x540 / 8192 points driven
     from pinned host buffers (uint8 images, point clouds, intrinsics, events) to host flow buffers, every step:
@@ -766,6 +801,11 @@ def main():
             ops_report["vs_ref_cuda"] = ref_cuda_column(cfg, stack, x, B, per_op, flush)
         except Exception as e:
             ops_report["vs_ref_cuda"] = {"error": repr(e)}
+    if rank == 0 and world == 1 and cfg.n_points <= 8192:
+        try:
+            ops_report["pointconv"] = pointconv_leg(cfg, x, B, dev)
+        except Exception as e:
+            ops_report["pointconv"] = {"error": repr(e)}
 
     # -------- end to end: every step copies ALL of its inputs from pinned host memory (copy stream, group by group
     # in dependency order) into one of two device input sets, replays the per-group CUDA graphs as the groups land,

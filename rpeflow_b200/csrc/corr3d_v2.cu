@@ -27,6 +27,17 @@
 #include "corr3d_common.cuh"
 #include "umma_common.cuh"
 
+#ifdef V2_TRACE
+// debug builds only (profiles/build_variant.sh trace "-DV2_TRACE"): clock64 stamps of CTA 0's first worker thread per tile
+__device__ long long v2_trace_buf[8 * 512];
+extern "C" __attribute__((visibility("default"))) int b200_debug_read_v2_trace(long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, v2_trace_buf, sizeof(long long) * n);
+}
+#define V2_STAMP(slot) do { if (blockIdx.x == 0 && tid == 0 && lt < 512) v2_trace_buf[lt * 8 + (slot)] = clock64(); } while (0)
+#else
+#define V2_STAMP(slot) do { } while (0)
+#endif
+
 namespace b200 {
 
 constexpr int V2_ROWS = 128, V2_KB = 32, V2_K = 16;
@@ -341,6 +352,7 @@ corr3d_v2_stage1_kernel(const float* __restrict__ xyz1, const float* __restrict_
         auto produce = [&](uint32_t item, uint32_t lt) {
             const uint32_t b = item / tiles;
             const int i0 = (int)(item - b * tiles) * 8;
+            V2_STAMP(0);
             // ---- meta: thread(s) of a row: neighbour index, offset, weight-net hidden layer
             {
                 const int i = min(i0 + (row >> 4), N1 - 1);
@@ -353,6 +365,10 @@ corr3d_v2_stage1_kernel(const float* __restrict__ xyz1, const float* __restrict_
                             z1 = __ldg(xyz1 + ((size_t)b * 3 + 2) * N1 + i);
                 if ((DEEP || V2_PREJ) && item + gridDim.x < items) fetch_j(item + gridDim.x);   // in flight until the next produce()
                 const float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+#ifdef V2_TRACE
+                if (dx == 123456.0f) s_d[row].w = dx;     // make the stamp below wait for the loads
+                V2_STAMP(1);
+#endif
                 uint8_t* hid = gbase + HID_OFF(lt % DEPTH);
                 if (NW == 8) {                              // two threads per row: `half` selects four of the eight outputs
                     float hd[4];
@@ -378,6 +394,7 @@ corr3d_v2_stage1_kernel(const float* __restrict__ xyz1, const float* __restrict_
                 if (half == 0) { s_j[row] = (int)j; s_d[row] = make_float4(dx, dy, dz, 0.0f); }
                 v2_worker_sync<NWT>();
             }
+            V2_STAMP(2);
             // ---- K blocks: this thread handles chunk q = tid & 7 of rows (step * NWT + tid) >> 3
             const int q = tid & 7;
             const float* a_base = A1 + (size_t)b * N1 * C + 4 * q;
@@ -456,14 +473,17 @@ corr3d_v2_stage1_kernel(const float* __restrict__ xyz1, const float* __restrict_
                     if (!(!resident && tid == 0)) v2_mbar_arrive(bar_full(s));
                 }
             }
+            V2_STAMP(3);
         };
 
         auto epilogue = [&](uint32_t item, uint32_t lt) {
             const uint32_t b = item / tiles;
             const int i0 = (int)(item - b * tiles) * 8;
             const uint32_t buf = nbuf == 2 ? (lt & 1u) : 0u, use = nbuf == 2 ? (lt >> 1) : lt;
+            V2_STAMP(4);
             v2_mbar_wait(bar_accf(buf), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            V2_STAMP(5);
             const uint32_t acc = tmem + buf * 2u * (uint32_t)C + ((uint32_t)(lq * 32) << 16);
             const int pt = i0 + lq * 2 + (lane >> 4);
             float* prow = P + ((size_t)b * N1 + min(pt, N1 - 1)) * C;
@@ -480,6 +500,7 @@ corr3d_v2_stage1_kernel(const float* __restrict__ xyz1, const float* __restrict_
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             v2_mbar_arrive(bar_acce(buf));
+            V2_STAMP(6);
         };
 
         // software pipeline over this CTA's tiles: with two accumulator buffers the operands of tile t+1 are produced

@@ -153,21 +153,23 @@ def _no_fallback(name, *tensors):
 def _correlation2d_nchw(input1, input2, max_displacement, negative_slope):
     """The single-pass NCHW route (b200_corr2d_fwd_nchw[_leaky]); None when the call is outside its limits."""
     needs_grad = torch.is_grad_enabled() and (input1.requires_grad or input2.requires_grad)
-    if needs_grad or int(max_displacement) != 4 or input1.dim() != 4 or input1.shape != input2.shape \
-            or input1.shape[3] % 4 != 0:
+    md = int(max_displacement)
+    if needs_grad or not 1 <= md <= 4 or input1.dim() != 4 or input1.shape != input2.shape:
         return None
     a, b = input1.contiguous().float(), input2.contiguous().float()
     B, C, H, W = a.shape
-    out = torch.empty((B, 81, H, W), dtype=torch.float32, device=a.device)
-    if a.data_ptr() % 16 or b.data_ptr() % 16 or out.data_ptr() % 16:
-        return None
+    out = torch.empty((B, (2 * md + 1) ** 2, H, W), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         if negative_slope is None:
-            check(lib.b200_corr2d_fwd_nchw(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, 4, _stream(a)),
-                  "b200_corr2d_fwd_nchw")
+            rc = lib.b200_corr2d_fwd_nchw(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, md, _stream(a))
+            name = "b200_corr2d_fwd_nchw"
         else:
-            check(lib.b200_corr2d_fwd_nchw_leaky(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, 4,
-                                                 float(negative_slope), _stream(a)), "b200_corr2d_fwd_nchw_leaky")
+            rc = lib.b200_corr2d_fwd_nchw_leaky(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, md, float(negative_slope),
+                                                _stream(a))
+            name = "b200_corr2d_fwd_nchw_leaky"
+    if rc == _lib.B200_ENOSUP:            # wide maps with rows TMA cannot address: the NHWC entry takes them
+        return None
+    check(rc, name)
     return out
 
 

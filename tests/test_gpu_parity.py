@@ -336,6 +336,28 @@ def test_corr2d_backward_levels_vs_oracle(C, H, W, monkeypatch):
     torch.testing.assert_close(g2, s2, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("B,C,H,W,md", [(3, 128, 18, 30, 4), (5, 192, 9, 15, 4), (2, 5, 7, 11, 4), (2, 20, 13, 50, 4), (1, 8, 6, 10, 2),
+                                        (2, 12, 9, 15, 1), (1, 33, 40, 250, 3), (2, 16, 12, 17, 4)])
+def test_corr2d_wrapper_call_on_narrow_maps_vs_oracle(B, C, H, W, md):
+    """correlation2d on NCHW maps whose rows TMA cannot address (W % 4 != 0: levels 4 and 5 of every configuration) and
+    other displacements: the shared-memory kernel behind b200_corr2d_fwd_nchw — no permutes — against the CPU oracle,
+    with and without the fused LeakyReLU, contiguous and 4-byte-offset (unaligned) inputs."""
+    rng = np.random.default_rng(B * 1000 + C + H + W)
+    f1 = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    f2 = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    want = spec.corr2d_fwd(nhwc(f1), nhwc(f2), md)
+    got = b200.correlation2d(cu(f1), cu(f2), md)
+    np.testing.assert_allclose(got.cpu().numpy(), want, **CORR_TOL)
+    if md == 4:
+        leaky = b200.correlation2d_leaky(cu(f1), cu(f2), md, 0.1)
+        np.testing.assert_allclose(leaky.cpu().numpy(), np.where(want > 0, want, 0.1 * want), **CORR_TOL)
+    pad1 = torch.zeros(f1.size + 1, device=DEV)
+    pad2 = torch.zeros(f2.size + 1, device=DEV)
+    u1 = pad1[1:].view(B, C, H, W).copy_(cu(f1))                       # storage offset of 4 bytes
+    u2 = pad2[1:].view(B, C, H, W).copy_(cu(f2))
+    np.testing.assert_allclose(b200.correlation2d(u1, u2, md).cpu().numpy(), want, **CORR_TOL)
+
+
 def test_corr2d_kat_reference_test_main():
     """KAT-corr (correlation_test.cpp:44-60,82-89): rand B=32,C=128,144x240, md=4; fwd + both grads, mean|d|<1e-6.
     Inputs drawn on the CPU generator (the reference draws on the device, which is not reproducible)."""
