@@ -55,10 +55,9 @@ B200_API int b200_corr2d_fwd(const float* in1_nhwc, const float* in2_nhwc, float
 /* a1 as the wrapper calls it (models/csrc/wrapper.py:55-72): the same cost volume straight from NCHW feature maps, so
  * the wrapper's two NCHW->NHWC permutes (wrapper.py:68-69) disappear.  Same result as b200_corr2d_fwd on the permuted
  * inputs up to fp32 summation order.
- *   in1, in2 : [B,C,H,W] fp32, NCHW contiguous                         out : [B,(2md+1)^2,H,W] fp32
- * md == 4, W % 4 == 0 and 16-byte aligned pointers take the TMA kernels; any other map with W <= 256 (the coarse pyramid
- * levels: W = 30, 15) and 1 <= md <= 4 takes a shared-memory kernel; wider unaligned maps return B200_ENOSUP (permute and
- * call b200_corr2d_fwd).
+ *   in1, in2 : [B,C,H,W] fp32, NCHW contiguous, 16-byte aligned        out : [B,81,H,W] fp32, 16-byte aligned
+ * Limits: md == 4 and W % 4 == 0 (TMA cannot address rows that are not 16-byte multiples); anything else returns
+ * B200_ENOSUP (permute and call b200_corr2d_fwd, as the reference's wrapper does).
  */
 B200_API int b200_corr2d_fwd_nchw(const float* in1_nchw, const float* in2_nchw, float* out_nchw,
                          int B, int C, int H, int W, int md, b200_stream_t stream);

@@ -276,12 +276,6 @@ cudaError_t corr2d_fwd_nchw(const float* in1, const float* in2, float* out, int 
 
 }  // namespace b200
 
-namespace b200 {
-bool corr2d_small_eligible(int B, int C, int H, int W, int md);                 // corr2d_small.cu: rows that TMA cannot address
-cudaError_t corr2d_fwd_small(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int md, float slope,
-                             cudaStream_t st);
-}  // namespace b200
-
 static int corr2d_fwd_nchw_entry(const char* who, const float* in1, const float* in2, float* out, int B, int C, int H, int W,
                                  int md, float slope, b200_stream_t stream) {
     using namespace b200;
@@ -291,13 +285,8 @@ static int corr2d_fwd_nchw_entry(const char* who, const float* in1, const float*
     B200_REQUIRE(slope >= 0.0f && slope <= 1.0f, "%s: negative_slope must be in [0,1] (got %g)", who, (double)slope);
     if (B == 0) return B200_OK;
     if (!corr2d_nchw_eligible(in1, in2, out, B, C, H, W, md)) {
-        if (corr2d_small_eligible(B, C, H, W, md)) {     // narrow maps of any width / alignment / md: shared-memory kernel
-            const cudaError_t es = corr2d_fwd_small(in1, in2, out, B, C, H, W, md, slope, as_stream(stream));
-            if (es != cudaSuccess) return cuda_fail(es, who);
-            return B200_OK;
-        }
-        set_error("%s: needs md=4, W %% 4 == 0 and 16-byte aligned pointers, or W <= 256 (permute to NHWC and call b200_corr2d_fwd "
-                  "otherwise)", who);
+        set_error("%s: needs md=4, W %% 4 == 0 and 16-byte aligned pointers (permute to NHWC and call b200_corr2d_fwd otherwise)",
+                  who);
         return B200_ENOSUP;
     }
     const cudaError_t e = corr2d_fwd_nchw(in1, in2, out, B, C, H, W, slope, as_stream(stream));

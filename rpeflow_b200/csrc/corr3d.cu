@@ -275,9 +275,14 @@ corr3d_stage2_kernel(const float* __restrict__ xyz1, const int64_t* __restrict__
 template <int KMAX>
 static cudaError_t launch_stage1(const float* xyz1, const float* xyz2, const int64_t* knn12, const Corr3dScratch& s,
                                  const b200_corr3d_weights* w, int B, int Cout, int N1, int N2, int k, cudaStream_t st) {
-    const int TP = 128 / k > 0 ? 128 / k : 1;
-    const int rows = TP * k;
-    const size_t smem = ((size_t)rows * (((Cout + 3) & ~3) + 4) + (size_t)rows * 8 + (size_t)rows * 4 + rows) * sizeof(float);
+    int TP = 128 / k > 0 ? 128 / k : 1;
+    auto smem_for = [&](int tp) {
+        const size_t r = (size_t)tp * k;
+        return (r * (((Cout + 3) & ~3) + 4) + r * 8 + r * 4 + r) * sizeof(float);
+    };
+    while (TP > 1 && smem_for(TP) > 200 * 1024) TP /= 2;      // wide layers (Cout > ~400): fewer points per CTA, not a launch error
+    if (smem_for(TP) > 227 * 1024) return cudaErrorInvalidConfiguration;
+    const size_t smem = smem_for(TP);
     auto kern = corr3d_stage1_kernel<KMAX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -304,6 +309,7 @@ extern "C" int b200_corr3d_fwd(const float* xyz1, const float* feat1, const floa
     B200_REQUIRE(Cout <= 512, "b200_corr3d_fwd: Cout=%d exceeds 512", Cout);
     B200_REQUIRE(B <= 65535, "b200_corr3d_fwd: B exceeds the grid limit");
     B200_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "b200_corr3d_fwd: scratch must be 16-byte aligned");
+    B200_REQUIRE(w != nullptr, "b200_corr3d_fwd: null weight struct");
     B200_REQUIRE(w->W1 && w->b1 && w->W2 && w->b2 && w->n1_Wa && w->n1_ba && w->n1_Wb && w->n1_bb && w->n1_Wc && w->n1_bc &&
                  w->n2_Wa && w->n2_ba && w->n2_Wb && w->n2_bb && w->n2_Wc && w->n2_bc, "b200_corr3d_fwd: null weight pointer");
     B200_REQUIRE(precision >= 0 && precision <= 2, "b200_corr3d_fwd: precision must be 0 (fp32), 1 (TF32) or 2 (3xTF32), got %d",

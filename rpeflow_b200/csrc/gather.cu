@@ -15,8 +15,8 @@
 namespace b200 {
 
 __device__ __forceinline__ int64_t wrap_index(int64_t j, int N, int* bad) {
-    if (j < 0) j += N;                                   // torch: negative indices wrap once
-    if (j < 0 || j >= N) {                               // torch would raise; we clamp and count
+    if (j < 0) j += N;                                   // python-style wrap of negative indices (torch.gather itself raises on them)
+    if (j < 0 || j >= N) {                               // torch would raise; we clamp and count (deliberate: see projection.py)
         if (bad) atomicAdd(bad, 1);
         j = j < 0 ? 0 : N - 1;
     }

@@ -275,7 +275,8 @@ extern "C" int b200_pointconv_fwd(const float* xyz, const float* feat, const flo
                                   int N, int S, int k, int precision, b200_stream_t stream) {
     using namespace b200;
     B200_REQUIRE((B == 0 || S == 0) || (xyz && sampled_xyz && knn && w && out && scratch && (feat || C == 0)), "b200_pointconv_fwd: null pointer");   // empty calls carry null pointers
-    B200_REQUIRE(w->Wa && w->ba && w->Wb && w->bb && w->L && w->bias, "b200_pointconv_fwd: null weight pointer");
+    B200_REQUIRE(w != nullptr || B == 0 || S == 0, "b200_pointconv_fwd: null weight struct");
+    B200_REQUIRE(w == nullptr || (w->Wa && w->ba && w->Wb && w->bb && w->L && w->bias), "b200_pointconv_fwd: null weight pointer");
     B200_REQUIRE(B >= 0 && C >= 0 && Cout >= 1 && N >= 1 && S >= 0, "b200_pointconv_fwd: bad sizes");
     B200_REQUIRE(B <= 65535, "b200_pointconv_fwd: B exceeds the grid limit");
     B200_REQUIRE(precision >= 0 && precision <= 2, "b200_pointconv_fwd: precision must be 0, 1 (TF32) or 2 (3xTF32), got %d", precision);

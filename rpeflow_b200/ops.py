@@ -167,7 +167,7 @@ def _correlation2d_nchw(input1, input2, max_displacement, negative_slope):
             rc = lib.b200_corr2d_fwd_nchw_leaky(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, C, H, W, md, float(negative_slope),
                                                 _stream(a))
             name = "b200_corr2d_fwd_nchw_leaky"
-    if rc == _lib.B200_ENOSUP:            # wide maps with rows TMA cannot address: the NHWC entry takes them
+    if rc == _lib.B200_ENOSUP:            # md != 4 or rows TMA cannot address (W % 4 != 0): the NHWC entry takes them
         return None
     check(rc, name)
     return out

@@ -30,6 +30,25 @@ def _prep_idx(idx, device):
     return idx.to(device=device, dtype=torch.int64).contiguous()
 
 
+# Deliberate deviation from the reference: the gather kernels wrap negative indices once (python / advanced-indexing
+# semantics; torch.gather itself raises on them) and CLAMP out-of-range ones instead of raising, because raising needs a
+# device-to-host sync per call.  With B200_CHECK_INDICES=1 every gather counts the indices it had to clamp and raises
+# IndexError like torch.gather does (one sync per call: a debugging aid for corrupt KNN / FPS outputs, not for production).
+import os as _os
+CHECK_INDICES = _os.environ.get("B200_CHECK_INDICES", "0") not in ("", "0")
+
+
+def _bad_counter(device):
+    return torch.zeros((1,), dtype=torch.int32, device=device) if CHECK_INDICES else None
+
+
+def _raise_if_bad(counter, what, n):
+    if counter is not None:
+        bad = int(counter.item())
+        if bad:
+            raise IndexError(f"rpeflow_b200.{what}: {bad} indices are out of range for a dimension of size {n}")
+
+
 def batch_indexing_channel_first(batched_data, batched_indices):
     """[B,C,N], [B,I1..Im] -> [B,C,I1..Im] (bit-exact move of 4-byte elements)."""
     assert batched_data.shape[0] == batched_indices.shape[0]
@@ -40,9 +59,11 @@ def batch_indexing_channel_first(batched_data, batched_indices):
     B, C, N = data.shape
     I = idx.numel() // max(B, 1)
     out = torch.empty((B, C, I), dtype=data.dtype, device=data.device)
+    bad = _bad_counter(data.device)
     with torch.cuda.device(data.device):
-        check(lib.b200_gather_cf(data.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, I, None, _stream(data)),
-              "b200_gather_cf")
+        check(lib.b200_gather_cf(data.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, I,
+                                 bad.data_ptr() if bad is not None else None, _stream(data)), "b200_gather_cf")
+    _raise_if_bad(bad, "batch_indexing_channel_first", N)
     return out.view([B, C] + list(idx.shape[1:]))
 
 
@@ -59,9 +80,11 @@ def batch_indexing_channel_last(batched_data, batched_indices):
     B, N, C = data.shape
     I = idx.numel() // max(B, 1)
     out = torch.empty((B, I, C), dtype=data.dtype, device=data.device)
+    bad = _bad_counter(data.device)
     with torch.cuda.device(data.device):
-        check(lib.b200_gather_cl(data.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, I, None, _stream(data)),
-              "b200_gather_cl")
+        check(lib.b200_gather_cl(data.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, I,
+                                 bad.data_ptr() if bad is not None else None, _stream(data)), "b200_gather_cl")
+    _raise_if_bad(bad, "batch_indexing_channel_last", N)
     shape = [B] + list(idx.shape[1:])
     return out.view(shape) if flat else out.view(shape + [C])
 

@@ -340,7 +340,7 @@ def test_corr2d_backward_levels_vs_oracle(C, H, W, monkeypatch):
                                         (2, 12, 9, 15, 1), (1, 33, 40, 250, 3), (2, 16, 12, 17, 4)])
 def test_corr2d_wrapper_call_on_narrow_maps_vs_oracle(B, C, H, W, md):
     """correlation2d on NCHW maps whose rows TMA cannot address (W % 4 != 0: levels 4 and 5 of every configuration) and
-    other displacements: the shared-memory kernel behind b200_corr2d_fwd_nchw — no permutes — against the CPU oracle,
+    other displacements (b200_corr2d_fwd_nchw answers B200_ENOSUP, the host mirror permutes and calls b200_corr2d_fwd) against the CPU oracle,
     with and without the fused LeakyReLU, contiguous and 4-byte-offset (unaligned) inputs."""
     rng = np.random.default_rng(B * 1000 + C + H + W)
     f1 = rng.standard_normal((B, C, H, W), dtype=np.float32)

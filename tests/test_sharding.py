@@ -52,6 +52,20 @@ def test_two_rank_sharding_over_gloo():
     assert torch.equal(whole["feat3d"][3][1][2:], r1["feat3d"][3][1])
 
 
+def test_strong_scaling_split_tiles_the_global_batch():
+    """bench.py --scaling strong: rank r of W takes the contiguous slice [r*G//W, (r+1)*G//W) of the global batch."""
+    for G in (74, 7, 8):
+        for W in (1, 2, 4, 8):
+            cuts = [(r * G // W, (r + 1) * G // W) for r in range(W)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == G
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(W - 1))
+            assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
+    whole = make_host_inputs(CONFIGS["tiny"], 3)
+    lo, hi = 1 * 3 // 2, 2 * 3 // 2                   # rank 1 of 2 at a global batch of 3
+    part = make_host_inputs(CONFIGS["tiny"], hi - lo, first_sample=lo)
+    assert torch.equal(whole["pcs"][lo:hi], part["pcs"])
+
+
 def test_census_matches_survey():
     w = census_work(CONFIGS["things"])
     assert w["knn_pairs"] == 535_756_288            # SURVEY §8(a4): 535.8 M pairs per sample at cfg1
