@@ -10,7 +10,11 @@
 // consecutive threads on the contiguous output axis (full 128-B store lines), point-major scratch for rows that
 // are later gathered so that gather reads are contiguous 128-bit loads, enough CTAs to fill 148 SMs by
 // splitting the channel loop over blockIdx.y when the point axis alone is too short.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
+#include "project_common.cuh"
 
 namespace b200 {
 
@@ -272,7 +276,6 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
 // (same taps, same arithmetic as grid_sample_pts_kernel), written as 64-byte runs from the compute lanes.  The model asks
 // for that tensor right after this call in four of its five fuser pairs per level (RPEFlow_core.py:31+53, :80+107,
 // :134+157), so sampling once here saves a second pass over the whole feature map.
-__host__ __device__ __forceinline__ int round4(int c) { return (c + 3) & ~3; }
 
 __global__ void __launch_bounds__(256)
 sample_point_major_kernel(const float* __restrict__ feat, const float* __restrict__ xy, const float* __restrict__ feat3d,
@@ -333,11 +336,11 @@ sample_point_major_kernel(const float* __restrict__ feat, const float* __restric
 // a slab of 32 feat3d channels of the nearest point (128-bit loads from the point's row of R, coalesced streaming stores).
 // Batch items are visited last-to-first: pass 1 has just streamed feat2d through L2 in ascending order, so the tail of
 // the batch is still resident when this kernel starts.
-constexpr int PN_SLAB = 32;
 
 __global__ void __launch_bounds__(256)
 project_nn_corr_kernel(const float* __restrict__ xy, const float* __restrict__ feat2d, const int64_t* __restrict__ nn,
                        const float* __restrict__ R, float* __restrict__ out, int C2, int C3, int H, int W, int N) {
+    const int role = blockIdx.z;
     const int b = gridDim.y - 1 - blockIdx.y;
     const int HW = H * W;
     const int p = blockIdx.x * 256 + threadIdx.x;
@@ -349,7 +352,7 @@ project_nn_corr_kernel(const float* __restrict__ xy, const float* __restrict__ f
     const int C2p = round4(C2), stride = C2p + round4(C3);
     const float* row = R + ((size_t)b * N + j) * stride;                // 16-byte aligned: stride % 4 == 0
 
-    if (blockIdx.z == 0) {
+    if (role == 0) {
         const float px = (float)(p % W), py = (float)(p / W);          // mesh_grid: x in channel 0 (models/utils.py:177-179)
         o[0] = __ldg(xy + ((size_t)b * 2 + 0) * N + j) - px;
         o[(size_t)HW] = __ldg(xy + ((size_t)b * 2 + 1) * N + j) - py;
@@ -369,29 +372,8 @@ project_nn_corr_kernel(const float* __restrict__ xy, const float* __restrict__ f
         o[(size_t)2 * HW] = __fdiv_rn(acc, (float)C2);                  // torch.mean over channels
         return;
     }
-    const int k0 = (blockIdx.z - 1) * PN_SLAB, k1 = min(k0 + PN_SLAB, C3);
-    const float* g = row + C2p;
-    int k = k0;
-    for (; k + 16 <= k1; k += 16) {                                     // 4 row loads in flight, 16 plane stores
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(g + k) + u);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            __stcs(o + (size_t)(3 + k + 4 * u + 0) * HW, v[u].x);
-            __stcs(o + (size_t)(3 + k + 4 * u + 1) * HW, v[u].y);
-            __stcs(o + (size_t)(3 + k + 4 * u + 2) * HW, v[u].z);
-            __stcs(o + (size_t)(3 + k + 4 * u + 3) * HW, v[u].w);
-        }
-    }
-    for (; k + 4 <= k1; k += 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(g + k));
-        __stcs(o + (size_t)(3 + k + 0) * HW, v.x);
-        __stcs(o + (size_t)(3 + k + 1) * HW, v.y);
-        __stcs(o + (size_t)(3 + k + 2) * HW, v.z);
-        __stcs(o + (size_t)(3 + k + 3) * HW, v.w);
-    }
-    for (; k < k1; ++k) __stcs(o + (size_t)(3 + k) * HW, __ldg(g + k));
+    const int k0 = (role - 1) * PN_SLAB, k1 = min(k0 + PN_SLAB, C3);
+    project_slab_copy(row + C2p, o, HW, k0, k1);
 }
 
 // f2: knn_interpolation (models/utils.py:140-156): out[b,c,q] = sum_s wn_s * feat[b,c,idx[b,q,s]], wn = normalised inverse
@@ -439,6 +421,24 @@ knn_interpolate_kernel(const float* __restrict__ in_xyz, const float* __restrict
             if (s < k) acc = __fadd_rn(acc, __fmul_rn(__ldg(fc + j[s]), w[s]));
         o[(size_t)c * Q] = acc;
     }
+}
+
+// project_tile.cu
+bool project_tile_eligible(const float* feat2d, const int64_t* nn, const float* out, int B, int C2, int C3, int H, int W, int N);
+cudaError_t project_tile_launch(const float* xy, const float* feat2d, const float* feat3d, const int64_t* nn, float* out,
+                                float* scratch, float* sampled_cf, int B, int C2, int C3, int H, int W, int N, cudaStream_t st);
+int64_t project_tile_extra_scratch_floats(int B, int N);
+
+// Which route a call takes.  B200_PROJECT_ROUTE = "two_pass" | "tiled" | unset (automatic), read per call: for ablations and tests.
+// Automatic: the tiled route where TMA can address the map and the cloud is dense enough that a pixel's nearest point
+// normally lies inside the 4-pixel halo (<= 16 pixels per point); small maps (pyramid levels 3-5 of a 960-wide image:
+// a few 60 x 32 tiles per sample cannot fill 148 persistent CTAs) stay on the two-pass kernels.
+static bool project_route_tiled(const float* feat2d, const int64_t* nn, const float* out, int B, int C2, int C3, int H, int W, int N) {
+    const char* v = getenv("B200_PROJECT_ROUTE");
+    const int forced = !v ? 0 : (strcmp(v, "two_pass") == 0 ? 1 : (strcmp(v, "tiled") == 0 ? 2 : 0));
+    if (forced == 1 || !project_tile_eligible(feat2d, nn, out, B, C2, C3, H, W, N)) return false;
+    if (forced == 2) return true;
+    return (int64_t)H * W >= 4096 && (int64_t)H * W <= (int64_t)16 * N;
 }
 
 static int pick_csplit(int64_t cols, int B, int C) {
@@ -530,7 +530,8 @@ extern "C" int b200_convex_upsample(const float* flow, const float* mask, float*
 
 extern "C" int64_t b200_project_nn_corr_scratch_floats(int B, int C2, int C3, int N) {
     if (B < 0 || C2 < 0 || C3 < 0 || N < 0) return 0;
-    return (int64_t)B * N * (b200::round4(C2) + b200::round4(C3));
+    // point-major rows [S | T] (both routes) + the tiled route's per-tile point lists
+    return (int64_t)B * N * (b200::round4(C2) + b200::round4(C3)) + b200::project_tile_extra_scratch_floats(B, N);
 }
 
 extern "C" int b200_project_nn_corr(const float* xy, const float* feat2d, const float* feat3d, const int64_t* nn,
@@ -549,6 +550,13 @@ extern "C" int b200_project_nn_corr_sampled(const float* xy, const float* feat2d
     B200_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "b200_project_nn_corr: scratch must be 16-byte aligned");
     if (B == 0) return B200_OK;
     cudaStream_t st = as_stream(stream);
+    if (project_route_tiled(feat2d, nn, out, B, C2, C3, H, W, N)) {
+        // one pass over feat2d (project_tile.cu): prep (T rows + per-tile point lists) -> tile kernel -> post (far pixels,
+        // sampled tensor to channel-first, feat3d slabs)
+        const cudaError_t e = project_tile_launch(xy, feat2d, feat3d, nn, out, scratch, sampled_cf, B, C2, C3, H, W, N, st);
+        if (e != cudaSuccess) return cuda_fail(e, "b200_project_nn_corr(tile)");
+        return B200_OK;
+    }
     sample_point_major_kernel<<<dim3(ceil_div(N, 16), B), 256, 0, st>>>(feat2d, xy, feat3d, scratch, sampled_cf, C2, C3, H, W, N);
     B200_LAUNCH_CHECK("b200_project_nn_corr(sample)");
     project_nn_corr_kernel<<<dim3(ceil_div((int64_t)H * W, 256), B, 1 + ceil_div(C3, PN_SLAB)), 256, 0, st>>>(

@@ -459,6 +459,56 @@ def test_project_nn_corr_golden_and_levels(golden):
         assert torch.equal(got[:, 3:].reshape(B, C3, -1), torch_ref.batch_indexing_channel_first(f3, nn))   # feat3d part is a pure gather
 
 
+@pytest.mark.parametrize("case", ["dense", "sparse", "crowded", "outside", "random_nn", "odd_channels", "small_map"])
+def test_project_nn_corr_tiled_route_equals_two_pass_and_oracle(case, monkeypatch):
+    """The single-pass tiled route (project_tile.cu) on inputs that stress its window logic: sparse clouds (nearest point
+    outside the 4-pixel halo -> per-tap global reads), every point in one tile (more points than threads), points far
+    outside the image / non-finite coordinates, arbitrary nn indices, channel counts that are no multiple of the 8-channel
+    stage, maps smaller than a tile.  Bars: 1e-5 vs the oracle; output AND sampled tensor bit-identical to
+    the two-pass kernels (same operation order)."""
+    from rpeflow_b200 import projection
+    gen = torch.Generator().manual_seed(500 + len(case))
+    B, C2, C3, H, W, N = {"dense": (3, 32, 32, 144, 240, 4096), "sparse": (2, 16, 8, 72, 120, 40), "crowded": (2, 24, 12, 48, 128, 1500),
+                          "outside": (2, 16, 16, 36, 60, 600), "random_nn": (2, 16, 20, 40, 64, 300),
+                          "odd_channels": (2, 81, 34, 72, 120, 2048), "small_map": (3, 13, 7, 5, 8, 30)}[case]
+    f2 = torch.randn(B, C2, H, W, generator=gen).to(DEV)
+    f3 = torch.randn(B, C3, N, generator=gen).to(DEV)
+    xy = torch.rand(B, 2, N, generator=gen) * torch.tensor([W - 1.0, H - 1.0]).view(1, 2, 1)
+    if case == "crowded":
+        xy = xy * torch.tensor([30.0 / W, 10.0 / H]).view(1, 2, 1) + torch.tensor([70.0, 18.0]).view(1, 2, 1)   # all inside one tile
+    if case == "outside":
+        xy = xy * 3.0 - torch.tensor([W * 1.0, H * 1.0]).view(1, 2, 1)
+        xy[0, 0, :5] = torch.tensor([float("nan"), float("inf"), -float("inf"), 1e30, -1e30])
+        xy[1, 1, 7] = float("nan")
+    xy = xy.to(DEV)
+    grid = torch_ref.pixel_grid(B, H, W).to(DEV)
+    if case == "random_nn":
+        nn = torch.randint(0, N, (B, H * W), generator=gen).to(DEV)
+    elif case == "outside":
+        finite = torch.nan_to_num(xy, nan=1e6, posinf=1e6, neginf=-1e6).clamp(-1e6, 1e6)
+        nn = b200.k_nearest_neighbor(finite, grid.contiguous(), 1)[..., 0]
+    else:
+        nn = b200.k_nearest_neighbor(xy, grid.contiguous(), 1)[..., 0]
+    res = {}
+    for route in ("two_pass", "tiled"):
+        monkeypatch.setenv("B200_PROJECT_ROUTE", route)
+        projection.SAMPLE_MEMO.clear()
+        out = b200.project_feat_with_nn_corr(xy, f2, f3, nn)
+        res[route] = (out, projection.SAMPLE_MEMO.take(f2, xy))
+        bare = b200.project_feat_with_nn_corr(xy, f2, f3, nn, keep_samples=False)
+        assert torch.equal(bare.view(torch.int32), out.view(torch.int32))
+    monkeypatch.delenv("B200_PROJECT_ROUTE")
+    projection.SAMPLE_MEMO.clear()
+    for a, b in zip(res["two_pass"], res["tiled"]):
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))                # bit patterns: NaN-safe comparison
+    plain = b200.grid_sample_wrapper(f2, xy)
+    assert torch.equal(plain.view(torch.int32), res["tiled"][1].view(torch.int32))
+    if case != "outside":                                                            # the C oracle is not asked about NaN coordinates
+        want = spec.project_nn_corr(xy.cpu().numpy(), f2.cpu().numpy(), f3.cpu().numpy(), nn.cpu().numpy())
+        np.testing.assert_allclose(res["tiled"][0].cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(res["tiled"][1].cpu().numpy(), spec.grid_sample_pts(f2.cpu().numpy(), xy.cpu().numpy()), rtol=1e-5, atol=1e-5)
+
+
 def test_projection_sampler_serves_the_following_grid_sample_bit_exactly():
     """project_feat_with_nn_corr(xy, f, ...) parks bilinear(f, xy); grid_sample_wrapper(f, xy) issued right after must return
     exactly what the stand-alone sampling kernel returns, exactly once, and never after an in-place write to f or xy."""
