@@ -121,19 +121,29 @@ event_voxel_trilinear_kernel(const float* __restrict__ xs, const float* __restri
     if (!(fabsf(x) < 1e9f) || !(fabsf(y) < 1e9f) || !(fabsf(tn) < 1e9f)) return;    // .int() of such values is masked out
     const int x0 = (int)x, y0 = (int)y, tq = (int)tn;                                // .int(): truncation (:545-547)
     float* g = vox + base;
+    // The two x taps of a (row, bin) pair are neighbours in memory: when the left one sits on an 8-byte boundary they go
+    // out as ONE red.global.add.v2.f32 (the kernel is bound by the SMs' RED issue rate — 1.5 M events x 8 taps at ~1.3
+    // cycles per lane — so every merged pair is a tap less; ncu r2).
+    const float wx0 = __fmul_rn(value, __fsub_rn(1.0f, fabsf(__fsub_rn((float)x0, x))));            // :557, left to right
+    const float wx1 = __fmul_rn(value, __fsub_rn(1.0f, fabsf(__fsub_rn((float)(x0 + 1), x))));
+    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
 #pragma unroll
-    for (int cx = 0; cx < 2; ++cx)
+    for (int cy = 0; cy < 2; ++cy)
 #pragma unroll
-        for (int cy = 0; cy < 2; ++cy)
-#pragma unroll
-            for (int ct = 0; ct < 2; ++ct) {
-                const int xl = x0 + cx, yl = y0 + cy, tl = tq + ct;
-                if (xl < 0 || xl >= W || yl < 0 || yl >= H || tl < 0 || tl >= bins) continue;   // :555-556
-                float w = __fmul_rn(value, __fsub_rn(1.0f, fabsf(__fsub_rn((float)xl, x))));    // :557-559, left to right
-                w = __fmul_rn(w, __fsub_rn(1.0f, fabsf(__fsub_rn((float)yl, y))));
-                w = __fmul_rn(w, __fsub_rn(1.0f, fabsf(__fsub_rn((float)tl, tn))));
-                atomicAdd(g + ((size_t)tl * H + yl) * W + xl, w);
+        for (int ct = 0; ct < 2; ++ct) {
+            const int yl = y0 + cy, tl = tq + ct;
+            if (yl < 0 || yl >= H || tl < 0 || tl >= bins) continue;                                  // :555-556
+            const float wy = __fsub_rn(1.0f, fabsf(__fsub_rn((float)yl, y)));
+            const float wt = __fsub_rn(1.0f, fabsf(__fsub_rn((float)tl, tn)));
+            const float a = __fmul_rn(__fmul_rn(wx0, wy), wt), b = __fmul_rn(__fmul_rn(wx1, wy), wt);   // :558-559
+            float* cell = g + ((size_t)tl * H + yl) * W + x0;
+            if (vx0 && vx1 && (reinterpret_cast<uintptr_t>(cell) & 7) == 0) {
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(cell), "f"(a), "f"(b) : "memory");
+            } else {
+                if (vx0) atomicAdd(cell, a);
+                if (vx1) atomicAdd(cell + 1, b);
             }
+        }
 }
 
 }  // namespace b200
