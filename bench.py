@@ -443,7 +443,9 @@ def roofline_report(cfg, work, per_op, B, peaks, traffic_db):
     for lvl in range(1, 6):
         hbm(f"corr2d_L{lvl}", f"corr2d_L{lvl}", work["corr2d_bytes"][lvl] * B, "corr2d_fwd_{diag,nchw}_kernel")
     for lvl in range(1, 6):
-        hbm(f"project_nn_corr_L{lvl}", f"project_nn_corr_L{lvl}", work["project_bytes"][lvl] * B, "sample_point_major_kernel + project_nn_corr_kernel")
+        hbm(f"project_nn_corr_L{lvl}", f"project_nn_corr_L{lvl}", work["project_bytes"][lvl] * B,
+            "project_prep_kernel + project_tile_kernel + project_post_kernel (maps of >= 4096 px TMA can address) / "
+            "sample_point_major_kernel + project_nn_corr_kernel (small maps)")
     for lvl in range(1, 6):
         hbm(f"grid_sample_L{lvl}", f"grid_sample_L{lvl}", work["grid_sample_bytes"][lvl] * B,
             "grid_sample_pts_kernel (4 of the 5 calls per level are served by the projection's sampler)")
@@ -783,7 +785,13 @@ def main():
         nn = _ops.k_nearest_neighbor(xy, stack.pixel_grid(B, h, w), 1)[..., 0]
         ms = time_isolated(lambda: projection.project_feat_with_nn_corr(xy, dec_2d, dec_3d, nn), flush)
         nb = project_bytes(96, 64, n, h, w) * B
-        iso = {"call": f"project_feat_with_nn_corr(C2=96, C3=64) at level {lvl}, batch {B} (2 launches)", "launch_ms": round(ms, 4),
+        iso = {"call": f"project_feat_with_nn_corr(C2=96, C3=64) at level {lvl}, batch {B} (3 launches)", "launch_ms": round(ms, 4),
+               "algorithmic_bytes": nb, "achieved": round(nb / (ms * 1e-3) / 1e9, 1), "frac": round(nb / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
+    elif top["op"] == "event_voxel":
+        one = {k: v[:1] for k, v in x.items() if k in ("events", "ev_x", "ev_y", "ev_t", "ev_p")}
+        ms = time_isolated(lambda: stack.voxelise(one), flush)
+        nb = work["event_voxel_bytes"]
+        iso = {"call": "event voxel grid of one sample (zero fill + scatter kernel), L2 flushed", "launch_ms": round(ms, 4),
                "algorithmic_bytes": nb, "achieved": round(nb / (ms * 1e-3) / 1e9, 1), "frac": round(nb / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
     roofline = {"kernel": f"{top['kernel']} ({top['op']}: the HBM-bound op with the largest share of the step, batch {B})",
                 "bound": "hbm", "achieved": top["achieved"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": top["frac"],
