@@ -47,7 +47,7 @@ B200_API const char* b200_last_error(void);      /* thread-local; "" if none    
  *   in1, in2 : [B,H,W,C] fp32, NHWC contiguous            out : [B,(2md+1)^2,H,W] fp32, NCHW
  *   out[b,(dy+md)*(2md+1)+(dx+md),y,x] = (1/C) * sum_c in1[b,y,x,c]*in2[b,y+dy,x+dx,c]; 0 outside the image.
  * Every output element is written (the caller does not need to zero `out`).
- * Limits: 1 <= md <= 4 (the model uses 4), C >= 1.
+ * Limits: 1 <= md <= 64, C >= 1.  md <= 4 takes the tuned kernels (the model uses 4); larger displacements a plain one.
  */
 B200_API int b200_corr2d_fwd(const float* in1_nhwc, const float* in2_nhwc, float* out_nchw,
                     int B, int C, int H, int W, int md, b200_stream_t stream);

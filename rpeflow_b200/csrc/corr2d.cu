@@ -15,6 +15,8 @@
 //   * stores: each thread writes 6 consecutive floats per displacement channel, the 4 strips of a row are contiguous.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -269,6 +271,61 @@ static cudaError_t launch_corr2d_bwd(const float* gout, const float* in1, const 
     return cudaGetLastError();
 }
 
+// ---- any max_displacement (md > 4): plain kernels, correctness first ---------------------------------------------------
+// The reference kernels take any md (correlation_forward_kernel.cu:11-55); RPEFlow only ever passes 4, so these are not
+// tuned: a warp per (pixel, displacement) with lanes over channels for the forward (coalesced NHWC rows), a thread per
+// (pixel, channel) for the backward.
+__global__ void __launch_bounds__(256)
+corr2d_fwd_any_kernel(const float* __restrict__ in1, const float* __restrict__ in2, float* __restrict__ out, int C, int H, int W,
+                      int md, int64_t items) {
+    const int D = 2 * md + 1;
+    const int lane = threadIdx.x & 31;
+    for (int64_t it = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); it < items; it += (int64_t)gridDim.x * 8) {
+        const int x = (int)(it % W);
+        int64_t r = it / W;
+        const int y = (int)(r % H); r /= H;
+        const int tc = (int)(r % (D * D));
+        const int b = (int)(r / (D * D));
+        const int dy = tc / D - md, dx = tc % D - md;
+        const int y2 = y + dy, x2 = x + dx;
+        float s = 0.0f;
+        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+            const float* a = in1 + (((size_t)b * H + y) * W + x) * C;
+            const float* c2 = in2 + (((size_t)b * H + y2) * W + x2) * C;
+            for (int c = lane; c < C; c += 32) s += __ldg(a + c) * __ldg(c2 + c);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        }
+        if (lane == 0) out[(((size_t)b * D * D + tc) * H + y) * W + x] = s / (float)C;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+corr2d_bwd_any_kernel(const float* __restrict__ gout, const float* __restrict__ in1, const float* __restrict__ in2,
+                      float* __restrict__ gin1, float* __restrict__ gin2, int C, int H, int W, int md, int64_t items) {
+    const int D = 2 * md + 1;
+    for (int64_t it = (int64_t)blockIdx.x * 256 + threadIdx.x; it < items; it += (int64_t)gridDim.x * 256) {
+        const int c = (int)(it % C);                          // channel fastest: NHWC partner reads coalesce
+        int64_t r = it / C;
+        const int x = (int)(r % W); r /= W;
+        const int y = (int)(r % H);
+        const int b = (int)(r / H);
+        float s1 = 0.0f, s2 = 0.0f;
+        for (int dy = -md; dy <= md; ++dy)
+            for (int dx = -md; dx <= md; ++dx) {
+                const int tc = (dy + md) * D + (dx + md);
+                const int y2 = y + dy, x2 = x + dx;            // grad wrt in1[y,x]: partner in2[y+dy,x+dx]
+                if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W)
+                    s1 += __ldg(gout + (((size_t)b * D * D + tc) * H + y) * W + x) * __ldg(in2 + (((size_t)b * H + y2) * W + x2) * C + c);
+                const int y1 = y - dy, x1 = x - dx;            // grad wrt in2[y,x]: partner in1[y-dy,x-dx]
+                if (y1 >= 0 && y1 < H && x1 >= 0 && x1 < W)
+                    s2 += __ldg(gout + (((size_t)b * D * D + tc) * H + y1) * W + x1) * __ldg(in1 + (((size_t)b * H + y1) * W + x1) * C + c);
+            }
+        gin1[(((size_t)b * C + c) * H + y) * W + x] = s1 / (float)C;
+        gin2[(((size_t)b * C + c) * H + y) * W + x] = s2 / (float)C;
+    }
+}
+
 }  // namespace b200
 
 extern "C" int b200_corr2d_fwd(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int md,
@@ -276,9 +333,16 @@ extern "C" int b200_corr2d_fwd(const float* in1, const float* in2, float* out, i
     using namespace b200;
     B200_REQUIRE((B == 0) || (in1 && in2 && out), "b200_corr2d_fwd: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "b200_corr2d_fwd: bad sizes B=%d C=%d H=%d W=%d", B, C, H, W);
-    B200_REQUIRE(md >= 1 && md <= 4, "b200_corr2d_fwd: max_displacement must be in [1,4] (got %d)", md);
+    B200_REQUIRE(md >= 1 && md <= 64, "b200_corr2d_fwd: max_displacement must be in [1,64] (got %d)", md);
     if (B == 0) return B200_OK;
     cudaError_t e;
+    if (md > 4) {                                             // not a shape RPEFlow uses: plain kernel
+        const int64_t items = (int64_t)B * (2 * md + 1) * (2 * md + 1) * H * W;
+        const int grid = (int)std::min<int64_t>((items + 7) / 8, (int64_t)sm_count() * 32);
+        corr2d_fwd_any_kernel<<<grid, 256, 0, as_stream(stream)>>>(in1, in2, out, C, H, W, md, items);
+        B200_LAUNCH_CHECK("b200_corr2d_fwd(any md)");
+        return B200_OK;
+    }
     if (corr2d_tma_eligible(in1, in2, B, C, H, W, md)) {
         e = corr2d_fwd_tma(in1, in2, out, B, C, H, W, as_stream(stream));
         if (e != cudaSuccess) return cuda_fail(e, "b200_corr2d_fwd(tma)");
@@ -299,10 +363,17 @@ extern "C" int b200_corr2d_bwd(const float* gout, const float* in1, const float*
     using namespace b200;
     B200_REQUIRE((B == 0) || (gout && in1 && in2 && gin1 && gin2), "b200_corr2d_bwd: null pointer");   // empty calls carry null pointers
     B200_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "b200_corr2d_bwd: bad sizes B=%d C=%d H=%d W=%d", B, C, H, W);
-    B200_REQUIRE(md >= 1 && md <= 4, "b200_corr2d_bwd: max_displacement must be in [1,4] (got %d)", md);
+    B200_REQUIRE(md >= 1 && md <= 64, "b200_corr2d_bwd: max_displacement must be in [1,64] (got %d)", md);
     B200_REQUIRE(H <= 65535 && B <= 65535, "b200_corr2d_bwd: H or B exceeds the grid limit");
     if (B == 0) return B200_OK;
     cudaError_t e;
+    if (md > 4) {
+        const int64_t items = (int64_t)B * H * W * C;
+        const int grid = (int)std::min<int64_t>((items + 255) / 256, (int64_t)sm_count() * 32);
+        corr2d_bwd_any_kernel<<<grid, 256, 0, as_stream(stream)>>>(gout, in1, in2, gin1, gin2, C, H, W, md, items);
+        B200_LAUNCH_CHECK("b200_corr2d_bwd(any md)");
+        return B200_OK;
+    }
     const char* old_kernel = getenv("B200_CORR2D_BWD_SIMPLE");          // measurement knob: "1" = the first, untiled kernel
     if (!(old_kernel && old_kernel[0] == '1') && corr2d_bwd_tiled_eligible(gout, in1, in2, gin1, gin2, B, C, H, W, md)) {
         e = corr2d_bwd_tiled(gout, in1, in2, gin1, gin2, B, C, H, W, as_stream(stream));

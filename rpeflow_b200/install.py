@@ -249,8 +249,8 @@ def patch_python_ops(patch_events=True, only=None):
         return ops.correlation2d(input1, input2, max_displacement)
 
     def correlation2d_ok(input1, input2, max_displacement, cpp_impl=True):
-        # md > 4 (not built at the extension entry) and odd ranks go to the reference wrapper and its torch loop
-        return cpp_impl and 1 <= int(max_displacement) <= 4 and input1.dim() == 4 and input1.shape == input2.shape
+        # odd ranks go to the reference wrapper and its torch loop (md > 4 is served by the plain any-displacement kernels)
+        return cpp_impl and 1 <= int(max_displacement) <= 64 and input1.dim() == 4 and input1.shape == input2.shape
 
     def k_nearest_neighbor(input_xyz, query_xyz, k, cpp_impl=True):
         return ops.k_nearest_neighbor(input_xyz, query_xyz, k)

@@ -50,7 +50,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.b200_fps(one, one, 1, 100, 100, None) == -1
     assert b"N > n_samples" in lib.b200_last_error()
     assert lib.b200_fps(one, one, 1, 100000, 10, None) == -3
-    assert lib.b200_corr2d_fwd(one, one, one, 1, 8, 4, 4, 5, None) == -1
+    assert lib.b200_corr2d_fwd(one, one, one, 1, 8, 4, 4, 65, None) == -1          # md in [1,64]: 5..64 take the plain kernel
     assert lib.b200_corr2d_fwd(None, one, one, 1, 8, 4, 4, 4, None) == -1
     assert lib.b200_event_voxel_int(one, 0, one, 5, 4, 4, 1, one, None) == -1
     assert lib.b200_corr3d_scratch_floats(2, 32, 32, 100, 100, 16) >= 3 * 2 * 100 * 32

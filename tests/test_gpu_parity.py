@@ -336,6 +336,25 @@ def test_corr2d_backward_levels_vs_oracle(C, H, W, monkeypatch):
     torch.testing.assert_close(g2, s2, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("B,C,H,W,md", [(2, 19, 11, 14, 5), (1, 40, 20, 16, 7)])
+def test_corr2d_large_displacements_vs_oracle(B, C, H, W, md):
+    """max_displacement > 4 (the reference kernels take any): the plain any-displacement kernels, forward through
+    correlation2d() and both gradients through autograd, against the CPU oracle."""
+    rng = np.random.default_rng(md * 100 + C)
+    f1 = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    f2 = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    go = rng.standard_normal((B, (2 * md + 1) ** 2, H, W), dtype=np.float32)
+    a, b = cu(f1).requires_grad_(True), cu(f2).requires_grad_(True)
+    out = b200.correlation2d(a, b, md)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), spec.corr2d_fwd(nhwc(f1), nhwc(f2), md), **CORR_TOL)
+    out.backward(cu(go))
+    g1, g2 = spec.corr2d_bwd(go, nhwc(f1), nhwc(f2), md)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), g1, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(b.grad.cpu().numpy(), g2, rtol=1e-5, atol=1e-5)
+    with torch.no_grad():
+        np.testing.assert_allclose(b200.correlation2d(cu(f1), cu(f2), md).cpu().numpy(), out.detach().cpu().numpy(), rtol=0, atol=0)
+
+
 @pytest.mark.parametrize("B,C,H,W,md", [(3, 128, 18, 30, 4), (5, 192, 9, 15, 4), (2, 5, 7, 11, 4), (2, 20, 13, 50, 4), (1, 8, 6, 10, 2),
                                         (2, 12, 9, 15, 1), (1, 33, 40, 250, 3), (2, 16, 12, 17, 4)])
 def test_corr2d_wrapper_call_on_narrow_maps_vs_oracle(B, C, H, W, md):

@@ -61,7 +61,7 @@ xy = torch.rand(1, 2, 7, requires_grad=True)
 f = torch.rand(1, 3, 6, 6)
 assert core.grid_sample_wrapper(f, xy).shape == (1, 3, 7)
 assert mu.project_feat_with_nn_corr(torch.rand(1, 2, 7), f, torch.rand(1, 4, 7)).shape == (1, 7, 6, 6)
-assert core.correlation2d(f, f, 5).shape == (1, 121, 6, 6)           # md > 4: the reference's own loop
+assert core.correlation2d(f, f, 5).shape == (1, 121, 6, 6)           # CPU tensors: the reference's own loop
 print('ROUNDTRIP-OK')
 """
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
