@@ -17,6 +17,8 @@
 //                                   x N=out x K8) into a TMEM accumulator that lives across the whole K loop.
 //                                   epilogue: tcgen05.ld, + bias, LeakyReLU(0.1), channel-first coalesced stores.
 // precision 1 = TF32 operands, 2 = 3xTF32 (hi/lo split of both operands, three MMAs: fp32-level accuracy).
+#include <stdlib.h>
+
 #include "umma_common.cuh"
 
 namespace b200 {
@@ -259,6 +261,17 @@ pointconv_tc_kernel(const float* __restrict__ xyz, const float* __restrict__ sam
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
 }
 
+// second generation (pointconv_v2.cu): 128 points per CTA, warp-specialised; this file's kernel stays as the route for
+// clouds of more than 65536 points and for A/B timing (B200_POINTCONV_V1=1)
+int pointconv_v2_run(const float* xyz, const float* feat, const float* sampled_xyz, const int64_t* knn,
+                     const b200_pointconv_weights* w, float* out, float* scratch, int B, int C, int Cout, int N, int S,
+                     int precision, cudaStream_t st);
+int64_t pointconv_v2_scratch_floats(int B, int C, int Cout, int N);
+static bool pc_force_v1() {
+    static const bool v = [] { const char* e = getenv("B200_POINTCONV_V1"); return e && e[0] == '1'; }();
+    return v;
+}
+
 static inline int pc_cp(int C) { return (C + 3 + 31) / 32 * 32; }
 static inline int pc_npad(int Cout) { return (Cout + 31) / 32 * 32; }      // 32: the epilogue reads 32 TMEM columns at a time
 
@@ -267,7 +280,9 @@ static inline int pc_npad(int Cout) { return (Cout + 31) / 32 * 32; }      // 32
 extern "C" int64_t b200_pointconv_scratch_floats(int B, int C, int Cout, int N) {
     if (B < 0 || C < 0 || Cout < 1 || N < 1) return 0;
     const int64_t cp = b200::pc_cp(C);
-    return (((int64_t)B * N * cp + 63) & ~int64_t(63)) + (int64_t)b200::pc_npad(Cout) * b200::PC_NW * cp;
+    const int64_t v1 = (((int64_t)B * N * cp + 63) & ~int64_t(63)) + (int64_t)b200::pc_npad(Cout) * b200::PC_NW * cp;
+    const int64_t v2 = b200::pointconv_v2_scratch_floats(B, C, Cout, N);
+    return v1 > v2 ? v1 : v2;
 }
 
 extern "C" int b200_pointconv_fwd(const float* xyz, const float* feat, const float* sampled_xyz, const int64_t* knn,
@@ -287,6 +302,8 @@ extern "C" int b200_pointconv_fwd(const float* xyz, const float* feat, const flo
     }
     if (B == 0 || S == 0) return B200_OK;
     cudaStream_t st = as_stream(stream);
+    if (N <= 65536 && !pc_force_v1())
+        return pointconv_v2_run(xyz, feat, sampled_xyz, knn, w, out, scratch, B, C, Cout, N, S, precision, st);
     const int Cp = pc_cp(C), Npad = pc_npad(Cout);
     float* Fpm = scratch;
     float* Lp = scratch + (((int64_t)B * N * Cp + 63) & ~int64_t(63));
