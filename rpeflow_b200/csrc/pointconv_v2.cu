@@ -13,8 +13,9 @@
 //     128-point weight table (133 KB), the rings and the index table share 227 KB.
 //   * 3xTF32 with the two halves of the B operand stacked along N: D[:, 0:N) += Ah.Bh + Al.Bh, D[:, N:2N) += Ah.Bl is two
 //     MMAs per k-step instead of three (out_channels <= 128; above that three MMAs); the halves are summed in the epilogue.
-//   * the Linear weight is re-laid once per call as one contiguous [out x 16] fp32 tile per K block; every worker thread
-//     fetches one float4 of the next K block's tile (L2-resident) ahead of its FMAs and writes its TF32 hi / lo parts.
+//   * the Linear weight is re-laid once per call as one contiguous [hi | lo] image per K block, already in the swizzled
+//     operand layout; one thread of warp 0 brings it into the stage with cp.async.bulk (expect_tx on the stage's "full"
+//     barrier) as soon as the stage is free; the weight-net outputs of the next K block are fetched under this block's FMAs.
 // precision 1 = TF32 operands, 2 (and 0) = 3xTF32.
 #include "umma_common.cuh"
 
@@ -197,11 +198,6 @@ pointconv_v2_kernel(const float* __restrict__ xyz, const float* __restrict__ sam
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = sbase + Ls.ring + s * stage_bytes, a_lo = a_hi + P2_A_TILE;
                 const uint32_t b_hi = a_hi + a_bytes, b_lo = b_hi + blo;
-#ifdef P2_EXP_NOMMA                                                // timing experiment: stages released without any MMA
-                p2_mbar_arrive(bars + 32u + 8u * s);
-                if (++s == (uint32_t)depth) { s = 0; ++ph; }
-                continue;
-#endif
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
                     const uint64_t ah = umma_desc_sw64(a_hi + ks * 32), bh = umma_desc_sw64(b_hi + ks * 32);
@@ -220,11 +216,7 @@ pointconv_v2_kernel(const float* __restrict__ xyz, const float* __restrict__ sam
                 umma_commit(bars + 32u + 8u * s);
                 if (++s == (uint32_t)depth) { s = 0; ++ph; }
             }
-#ifdef P2_EXP_NOMMA
-            p2_mbar_arrive(bar_accf);
-#else
             umma_commit(bar_accf);
-#endif
         }
         __syncwarp();
     } else {
@@ -281,11 +273,8 @@ pointconv_v2_kernel(const float* __restrict__ xyz, const float* __restrict__ sam
         float4 wc[4];
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) wc[k4] = wt4[k4];
-        float f[P2_K][4];
         for (int cb = 0; cb < ncb; ++cb) {
-#ifdef P2_EXP_NOGATHER
-            if (cb == 0)
-#endif
+            float f[P2_K][4];
             {
                 const uint4 j0 = *reinterpret_cast<const uint4*>(s_j + p * P2_K), j1 = *reinterpret_cast<const uint4*>(s_j + p * P2_K + 8);
                 const uint32_t jw[8] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w};
@@ -298,15 +287,11 @@ pointconv_v2_kernel(const float* __restrict__ xyz, const float* __restrict__ sam
             }
 #pragma unroll 1
             for (int w = 1; w <= P2_NW; ++w) {
-                p2_mbar_wait(bar_f + 32u, par_e);               // the MMAs that read this stage are done
-                if (warp == 0) {                                // one thread starts the bulk copy of the block's B tile into the stage
+                if (warp == 0) {                                // warp 0 takes the stage first: one thread starts the bulk copy of the B tile
+                    p2_mbar_wait(bar_f + 32u, par_e);           // the MMAs that read this stage are done
                     if (lane == 0) {
-#ifdef P2_EXP_NOCOPY                                               // timing experiment: no B tile traffic (results wrong)
-                        p2_mbar_arrive(bar_f);
-#else
                         p2_mbar_arrive_tx(bar_f, b_bytes);
                         p2_bulk_g2s(bdst, bsrc, b_bytes, bar_f);
-#endif
                     }
                     bsrc += b_bytes;
                 }
@@ -321,6 +306,7 @@ pointconv_v2_kernel(const float* __restrict__ xyz, const float* __restrict__ sam
                         for (int c = 0; c < 4; ++c) acc[c] = fmaf(ws[u], f[k4 * 4 + u][c], acc[c]);
                     wc[k4] = wnx[k4];
                 }
+                if (warp != 0) p2_mbar_wait(bar_f + 32u, par_e);    // the other warps need the stage only now, after their FMAs
                 if (SPLIT) {
                     const float4 hi = make_float4(tf32_hi(acc[0]), tf32_hi(acc[1]), tf32_hi(acc[2]), tf32_hi(acc[3]));
                     *reinterpret_cast<float4*>(st) = hi;
@@ -328,9 +314,7 @@ pointconv_v2_kernel(const float* __restrict__ xyz, const float* __restrict__ sam
                 } else {
                     *reinterpret_cast<float4*>(st) = make_float4(acc[0], acc[1], acc[2], acc[3]);
                 }
-#ifndef P2_EXP_NOFENCE
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
                 __syncwarp();
                 if (lane == 0) p2_mbar_arrive(bar_f);
                 if (++s == (uint32_t)depth) { s = 0; par_e ^= 1u; st = st0; bdst = bdst0; bar_f = bars; }
@@ -374,11 +358,7 @@ template <int MODE>
 static int p2_launch(const float* xyz, const float* sampled, const int64_t* knn, const float* Fpm, const float* Limg,
                      const b200_pointconv_weights* w, float* out, int B, int Cp, int N, int S, int Cout, int Npad, cudaStream_t st) {
     const int split = MODE != 0;
-#ifdef P2_EXP_DEPTH
-    int depth = P2_EXP_DEPTH;
-#else
     int depth = 4;
-#endif
     while (depth > 1 && p2_layout(Npad, split, depth).total + 1024 > P2_SMEM_MAX) --depth;
     const size_t smem = (size_t)p2_layout(Npad, split, depth).total + 1024;
     if (smem > (size_t)P2_SMEM_MAX) {
