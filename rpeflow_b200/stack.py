@@ -299,17 +299,26 @@ class HostFeeder:
     copy stream, group by group in dependency order (small point data first, the level-1 activations last), and
     records one event per group so the compute stream only waits for what the next stage reads."""
 
-    def __init__(self, host, device, depth=2):
+    EXTERNAL = ("pcs", "events", "ev_x", "ev_y", "ev_t", "ev_p")      # what reaches the path from outside the model
+
+    def __init__(self, host, device, depth=2, resident=None):
+        """`resident`: a device input tree; when given, only the EXTERNAL inputs (point clouds, raw events) get per-slot device
+        buffers and per-step copies, everything else (the feature maps the model computes on the device) is shared from it."""
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
-        self.slots = [_map_tensors(host, lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device))
-                      for _ in range(depth)]
+        if resident is None:
+            self.slots = [_map_tensors(host, lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device))
+                          for _ in range(depth)]
+        else:
+            self.slots = [{k: (v.clone() if k in self.EXTERNAL else v) for k, v in resident.items()} for _ in range(depth)]
         src = group_tensors(host)
         self.plan = []
         for slot in self.slots:
             dst = group_tensors(slot)
-            self.plan.append([(name, list(zip(dst[name], src[name]))) for name in INPUT_GROUPS])
-        self.nbytes = tensors_nbytes(host)
+            own = None if resident is None else {slot[k].data_ptr() for k in self.EXTERNAL if k in slot}
+            self.plan.append([(name, [(d, s_) for d, s_ in zip(dst[name], src[name]) if own is None or d.data_ptr() in own])
+                              for name in INPUT_GROUPS])
+        self.nbytes = sum(s_.numel() * s_.element_size() for _, pairs in self.plan[0] for _, s_ in pairs)
 
     def issue(self, slot, after=None):
         """Enqueue the copies into device set `slot` (after event `after`, e.g. the last compute that read that

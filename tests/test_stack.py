@@ -64,6 +64,22 @@ def test_graph_replay_and_feeder_match_eager_run():
         assert _same({k: v for k, v in out.items() if k != "event_voxel"}, want)
         assert torch.equal(runners[slot].checksum[0], ints_w)
 
+    # external inputs only (point clouds + raw events) streamed per step, the feature maps shared from the resident set
+    del runners, feeder
+    ext = HostFeeder(host, dev, depth=2, resident=x)
+    assert 0 < ext.nbytes < sum(t.numel() * t.element_size() for ts in __import__("rpeflow_b200.stack", fromlist=["x"]).group_tensors(host).values() for t in ts)
+    assert all(sl["pcs"].data_ptr() != x["pcs"].data_ptr() and sl["feat2d"] is x["feat2d"] for sl in ext.slots)
+    runners = [GraphedStack(stack, slot, fused=False) for slot in ext.slots]
+    for step in range(3):
+        slot = step % 2
+        ext.slots[slot]["pcs"].fill_(float("nan"))           # poison the per-slot buffer: the copy must refill it
+        main.synchronize()
+        evs = ext.issue(slot)
+        out = runners[slot].replay(wait=lambda g, evs=evs: main.wait_event(evs[g]))
+        main.synchronize()
+        assert _same({k: v for k, v in out.items() if k != "event_voxel"}, want)
+        assert torch.equal(runners[slot].checksum[0], ints_w)
+
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["dsec", "hd", "hd_scaled"])
