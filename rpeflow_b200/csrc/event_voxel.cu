@@ -121,6 +121,7 @@ event_voxel_trilinear_kernel(const float* __restrict__ xs, const float* __restri
     if (!(fabsf(x) < 1e9f) || !(fabsf(y) < 1e9f) || !(fabsf(tn) < 1e9f)) return;    // .int() of such values is masked out
     const int x0 = (int)x, y0 = (int)y, tq = (int)tn;                                // .int(): truncation (:545-547)
     float* g = vox + base;
+    const float* vox_end = vox + (size_t)bins * (polarity ? 2 : 1) * H * W;
     // The two x taps of a (row, bin) pair are neighbours in memory: when the left one sits on an 8-byte boundary they go
     // out as ONE red.global.add.v2.f32 (the kernel is bound by the SMs' RED issue rate — 1.5 M events x 8 taps at ~1.3
     // cycles per lane — so every merged pair is a tap less; ncu r2).
@@ -137,8 +138,13 @@ event_voxel_trilinear_kernel(const float* __restrict__ xs, const float* __restri
             const float wt = __fsub_rn(1.0f, fabsf(__fsub_rn((float)tl, tn)));
             const float a = __fmul_rn(__fmul_rn(wx0, wy), wt), b = __fmul_rn(__fmul_rn(wx1, wy), wt);   // :558-559
             float* cell = g + ((size_t)tl * H + yl) * W + x0;
-            if (vx0 && vx1 && (reinterpret_cast<uintptr_t>(cell) & 7) == 0) {
+            const uintptr_t ca = reinterpret_cast<uintptr_t>(cell);
+            if (vx0 && vx1 && (ca & 7) == 0) {
                 asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(cell), "f"(a), "f"(b) : "memory");
+            } else if (vx0 && vx1 && (ca & 15) == 4 && cell > vox && cell + 2 < vox_end) {
+                // the pair sits in the middle of a 16-byte group: one v4 with zeros on the outer lanes (x + 0 = x) instead of two
+                // scalar REDs; the outer lanes are this row's neighbours or, at a row end, the next row's first cell
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cell - 1), "f"(0.0f), "f"(a), "f"(b), "f"(0.0f) : "memory");
             } else {
                 if (vx0) atomicAdd(cell, a);
                 if (vx1) atomicAdd(cell + 1, b);
