@@ -38,9 +38,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=74,
-                    help="frame pairs per GPU per step (74 pairs = 148 clouds: one FPS cloud per SM of a B200); with "
-                         "--scaling strong it is the GLOBAL batch, split over the GPUs")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="frame pairs per GPU per step (default workload.BENCH_BATCH = 148 pairs = 296 clouds: two FPS chains per "
+                         "SM of a B200; 74 = one per SM); with --scaling strong it is the GLOBAL batch, split over the GPUs")
     ap.add_argument("--workload", default="things", choices=["things", "dsec", "hd", "hd_scaled", "tiny"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -688,6 +688,8 @@ def main():
     args = parse()
     _claim_stdout()
     meta = baseline_meta()
+    if args.batch is None:
+        args.batch = load_workload_module().DEFAULT_BATCH[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, meta)
         return

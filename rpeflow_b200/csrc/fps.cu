@@ -171,12 +171,23 @@ __device__ __forceinline__ unsigned fps_spread5(unsigned v) {         // 5 bits 
     return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
 }
 
-template <int PPT, int FP_T>
-__global__ void __launch_bounds__(FP_T, 1)
+// SM = true: the sorted coordinates live in SHARED memory instead of registers (only the running distances stay in
+// registers), so the kernel fits 64 registers and 112 KB and TWO clouds share an SM: an iteration is a latency chain that
+// leaves the SM mostly idle, and with more clouds than SMs (batch > 74 on a B200) the second wave costs nothing extra.
+// Visited rows (a few per iteration after pruning) read their coordinates with three conflict-free LDS.  Same arithmetic,
+// same results.
+template <int PPT, int FP_T, bool SM>
+__global__ void __launch_bounds__(FP_T, SM ? 2 : 1)
 fps_pruned_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int N, int S) {
     constexpr int NP = PPT * FP_T, NW = FP_T / 32, RS = NW * 32;     // RS: slots between consecutive rows of a thread
     static_assert(PPT % 4 == 0 && PPT <= 32 && NP <= 8192, "rows are tested by lanes and visited in groups of four");
-    __shared__ unsigned s_key[NP];                       // sort keys, then the original index of every sorted slot
+    __shared__ unsigned s_key_static[SM ? 1 : NP];       // sort keys, then the original index of every sorted slot
+    extern __shared__ __align__(16) unsigned char fps_dyn[];          // SM: [keys -> x | y | z | idx16]
+    unsigned* s_key = SM ? reinterpret_cast<unsigned*>(fps_dyn) : s_key_static;
+    float* s_x = reinterpret_cast<float*>(fps_dyn);      // aliases the keys: written after every key has been read
+    float* s_y = s_x + NP;
+    float* s_z = s_y + NP;
+    unsigned short* s_i16 = reinterpret_cast<unsigned short*>(s_z + NP);
     __shared__ float s_red[6][NW];
     __shared__ unsigned s_d[2][NW], s_i[2][NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -233,8 +244,9 @@ fps_pruned_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int 
 
     // registers: row i of this thread = sorted slot (i*NW + warp)*32 + lane, i.e. bucket i*NW + warp — neighbouring
     // buckets (the ones a new centre activates together) belong to different warps, so the visits spread over the CTA
-    float px[PPT], py[PPT], pz[PPT], dist[PPT];
-    unsigned* my_idx = s_key + warp * 32 + lane;         // my_idx[i*RS]: original index of row i's point (0xFFFFFFFF: none)
+    float px[SM ? 1 : PPT], py[SM ? 1 : PPT], pz[SM ? 1 : PPT], dist[PPT];
+    const int base = warp * 32 + lane;
+    unsigned* my_idx = s_key + base;                     // my_idx[i*RS]: original index of row i's point (0xFFFFFFFF: none)
     float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f, rmax_d = 0.0f;
     unsigned rmax_i = 0xFFFFFFFFu;
     bool rstale = false;                                 // rmax_i is recomputed lazily, only for a row that holds the warp's max
@@ -243,17 +255,19 @@ fps_pruned_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int 
         const unsigned key = my_idx[i * RS];
         const bool ok = key != 0xFFFFFFFFu;
         const unsigned oi = ok ? (key & 8191u) : 0xFFFFFFFFu;
-        px[i] = ok ? __ldg(P + (size_t)oi * 3 + 0) : 0.0f;
-        py[i] = ok ? __ldg(P + (size_t)oi * 3 + 1) : 0.0f;
-        pz[i] = ok ? __ldg(P + (size_t)oi * 3 + 2) : 0.0f;
+        const float x = ok ? __ldg(P + (size_t)oi * 3 + 0) : 0.0f;
+        const float y = ok ? __ldg(P + (size_t)oi * 3 + 1) : 0.0f;
+        const float z = ok ? __ldg(P + (size_t)oi * 3 + 2) : 0.0f;
+        if (SM) { s_y[i * RS + base] = y; s_z[i * RS + base] = z; s_i16[i * RS + base] = (unsigned short)(ok ? oi : 0xFFFFu); }
+        else { px[i] = x; py[i] = y; pz[i] = z; }
         dist[i] = ok ? 1e10f : 0.0f;
         // row box over the lanes that hold a point; an empty row gets (+big, -big): its gap is huge, it is never visited
-        const float bx0 = fps_unorder(__reduce_min_sync(FULL, fps_orderable(ok ? px[i] : 3.0e38f)));
-        const float by0 = fps_unorder(__reduce_min_sync(FULL, fps_orderable(ok ? py[i] : 3.0e38f)));
-        const float bz0 = fps_unorder(__reduce_min_sync(FULL, fps_orderable(ok ? pz[i] : 3.0e38f)));
-        const float bx1 = fps_unorder(__reduce_max_sync(FULL, fps_orderable(ok ? px[i] : -3.0e38f)));
-        const float by1 = fps_unorder(__reduce_max_sync(FULL, fps_orderable(ok ? py[i] : -3.0e38f)));
-        const float bz1 = fps_unorder(__reduce_max_sync(FULL, fps_orderable(ok ? pz[i] : -3.0e38f)));
+        const float bx0 = fps_unorder(__reduce_min_sync(FULL, fps_orderable(ok ? x : 3.0e38f)));
+        const float by0 = fps_unorder(__reduce_min_sync(FULL, fps_orderable(ok ? y : 3.0e38f)));
+        const float bz0 = fps_unorder(__reduce_min_sync(FULL, fps_orderable(ok ? z : 3.0e38f)));
+        const float bx1 = fps_unorder(__reduce_max_sync(FULL, fps_orderable(ok ? x : -3.0e38f)));
+        const float by1 = fps_unorder(__reduce_max_sync(FULL, fps_orderable(ok ? y : -3.0e38f)));
+        const float bz1 = fps_unorder(__reduce_max_sync(FULL, fps_orderable(ok ? z : -3.0e38f)));
         const unsigned any = __reduce_min_sync(FULL, oi);
         if (lane == i) {
             lox = bx0; loy = by0; loz = bz0; hix = bx1; hiy = by1; hiz = bz1;
@@ -262,10 +276,18 @@ fps_pruned_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int 
         }
     }
     __syncthreads();                                     // every key has been read before the slots are rewritten
+    if (SM) {
 #pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-        const unsigned key = my_idx[i * RS];
-        my_idx[i * RS] = key != 0xFFFFFFFFu ? (key & 8191u) : 0xFFFFFFFFu;
+        for (int i = 0; i < PPT; ++i) {                  // x goes where the keys were
+            const unsigned oi = s_i16[i * RS + base];
+            s_x[i * RS + base] = oi != 0xFFFFu ? __ldg(P + (size_t)oi * 3 + 0) : 0.0f;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const unsigned key = my_idx[i * RS];
+            my_idx[i * RS] = key != 0xFFFFFFFFu ? (key & 8191u) : 0xFFFFFFFFu;
+        }
     }
     __syncwarp();                                        // a thread only ever reads its own slots again
 
@@ -288,7 +310,8 @@ fps_pruned_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int 
 #pragma unroll
             for (int i = g4; i < g4 + 4; ++i) {
                 if (!((mask >> i) & 1u)) continue;       // warp-uniform
-                const float d = sqdist3_rule(px[i], py[i], pz[i], cx, cy, cz);
+                const float d = SM ? sqdist3_rule(s_x[i * RS + base], s_y[i * RS + base], s_z[i * RS + base], cx, cy, cz)
+                                   : sqdist3_rule(px[SM ? 0 : i], py[SM ? 0 : i], pz[SM ? 0 : i], cx, cy, cz);
                 dist[i] = fminf(dist[i], d);
                 const unsigned m = __reduce_max_sync(FULL, __float_as_uint(dist[i]));   // >= +0: bit order = value order
                 if (lane == i) { rmax_d = __uint_as_float(m); rstale = true; }
@@ -304,7 +327,8 @@ fps_pruned_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int 
 #pragma unroll
                 for (int i = g4; i < g4 + 4; ++i) {
                     if (!((need >> i) & 1u)) continue;
-                    const unsigned mi = __reduce_min_sync(FULL, __float_as_uint(dist[i]) == wmax ? my_idx[i * RS] : 0xFFFFFFFFu);
+                    const unsigned mine = SM ? (s_i16[i * RS + base] == 0xFFFFu ? 0xFFFFFFFFu : (unsigned)s_i16[i * RS + base]) : my_idx[SM ? 0 : i * RS];
+                    const unsigned mi = __reduce_min_sync(FULL, __float_as_uint(dist[i]) == wmax ? mine : 0xFFFFFFFFu);
                     if (lane == i) { rmax_i = mi; rstale = false; }
                 }
             }
@@ -323,9 +347,17 @@ fps_pruned_kernel(const float* __restrict__ xyz, int64_t* __restrict__ out, int 
     }
 }
 
-template <int PPT, int FP_T>
+template <int PPT, int FP_T, bool SM = false>
 static cudaError_t launch_fps_pruned(const float* xyz, int64_t* idx, int B, int N, int S, cudaStream_t st) {
-    fps_pruned_kernel<PPT, FP_T><<<B, FP_T, 0, st>>>(xyz, idx, N, S);
+    size_t smem = 0;
+    if (SM) {
+        smem = (size_t)PPT * FP_T * (3 * sizeof(float) + sizeof(unsigned short));
+        cudaError_t e = cudaFuncSetAttribute(fps_pruned_kernel<PPT, FP_T, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fps_pruned_kernel<PPT, FP_T, SM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+    }
+    fps_pruned_kernel<PPT, FP_T, SM><<<B, FP_T, smem, st>>>(xyz, idx, N, S);
     return cudaGetLastError();
 }
 
@@ -333,7 +365,12 @@ static cudaError_t dispatch_pruned(const float* xyz, int64_t* idx, int B, int N,
     if (N <= 1024) return launch_fps_pruned<4, 256>(xyz, idx, B, N, S, st);
     if (N <= 2048) return launch_fps_pruned<4, 512>(xyz, idx, B, N, S, st);
     if (N <= 4096) return launch_fps_pruned<8, 512>(xyz, idx, B, N, S, st);
-    if (const char* t = getenv("B200_FPS_T")) { if (t[0] == '2') return launch_fps_pruned<32, 256>(xyz, idx, B, N, S, st); if (t[0] == '1') return launch_fps_pruned<8, 1024>(xyz, idx, B, N, S, st); }
+    const char* t = getenv("B200_FPS_T");                // measurement / test knob: 1, 2 = other shapes, 3 / 0 = force / forbid the shared variant
+    if (t && t[0] == '2') return launch_fps_pruned<32, 256>(xyz, idx, B, N, S, st);
+    if (t && t[0] == '1') return launch_fps_pruned<8, 1024>(xyz, idx, B, N, S, st);
+    if (t && t[0] == '4') return launch_fps_pruned<32, 256, true>(xyz, idx, B, N, S, st);
+    // more clouds than SMs: two clouds per SM (coordinates in shared memory) instead of a second wave
+    if ((B > sm_count() && !(t && t[0] == '0')) || (t && t[0] == '3')) return launch_fps_pruned<16, 512, true>(xyz, idx, B, N, S, st);
     return launch_fps_pruned<16, 512>(xyz, idx, B, N, S, st);
 }
 

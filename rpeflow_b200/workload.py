@@ -10,6 +10,10 @@ import torch
 
 LEVEL_CHANNELS = [32, 64, 96, 128, 192]          # levels 1..5 (pwc2d_core.py:28-40 / pwc3d_core.py:44-57)
 PYRAMID_POINTS = [4096, 2048, 1024, 512, 256]    # RPEFlow.py:74 (hard-coded)
+# bench.py's default frame pairs per GPU per step: 148 pairs = 296 point clouds = two FPS chains per SM of a B200 (the
+# two-clouds-per-SM FPS kernel); round 1 and most of round 2 measured 74 (one cloud per SM)
+BENCH_BATCH = 148
+DEFAULT_BATCH = {"things": BENCH_BATCH, "dsec": BENCH_BATCH, "hd": 18, "hd_scaled": 18, "tiny": 4}   # hd: 36 clouds x 4-CTA clusters
 
 
 @dataclass

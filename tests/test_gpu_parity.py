@@ -263,6 +263,24 @@ def test_fps_forced_cluster(monkeypatch):
         np.testing.assert_array_equal(b200.ops._furthest_point_sampling_cuda(cu(xyz), 512).cpu().numpy(), want)
 
 
+def test_fps_two_clouds_per_sm_variant(monkeypatch):
+    """Coordinates in shared memory, two clouds per SM (taken when a call has more clouds than SMs; B200_FPS_T=3 forces it,
+    =0 forbids it): same picks as the oracle and as the register-resident kernel, with and without padding slots."""
+    rng = np.random.default_rng(31)
+    for n in (8192, 5003):
+        xyz = (rng.random((3, n, 3), dtype=np.float32) * np.array([40.0, 25.0, 80.0], dtype=np.float32)).astype(np.float32)
+        xyz[1, 100:400] = xyz[1, 7]                                     # duplicates: index tie-breaks
+        want = spec.fps(xyz, 700)
+        monkeypatch.setenv("B200_FPS_T", "3")
+        np.testing.assert_array_equal(b200.ops._furthest_point_sampling_cuda(cu(xyz), 700).cpu().numpy(), want)
+        monkeypatch.delenv("B200_FPS_T")
+    g = torch.Generator().manual_seed(5)
+    many = (torch.rand(300, 8192, 3, generator=g) * torch.tensor([30.0, 17.0, 90.0])).to(DEV)      # > 148 clouds: the natural dispatch
+    a = b200.ops._furthest_point_sampling_cuda(many, 4096)
+    monkeypatch.setenv("B200_FPS_T", "0")
+    assert torch.equal(a, b200.ops._furthest_point_sampling_cuda(many, 4096))
+
+
 def test_fps_pyramid_prefix_property():
     """build_pc_pyramid (pwc3d_core.py:8-28): levels are prefixes of one 4096-long list; cfg3 batch."""
     g = torch.Generator().manual_seed(4)

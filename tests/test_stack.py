@@ -114,15 +114,17 @@ def test_other_baseline_configs_run_and_index_ops_stay_exact(name):
 
 @pytest.mark.gpu
 def test_bench_batch_graph_replay_matches_the_oracle_on_first_and_last_sample():
-    """The shapes bench.py times: one CUDA-graph replay of the whole census over 74 frame pairs (persistent corr2d CTAs
-    walking thousands of tiles, 148-cloud FPS, multi-tile Correlation3D CTAs).  Samples 0 and 73 of every output are
-    compared with the CPU oracle: indices exactly, floats at the SURVEY §8a tolerances."""
+    """The shapes bench.py times: one CUDA-graph replay of the whole census over the bench batch (148 frame pairs: persistent
+    corr2d CTAs walking thousands of tiles, 296-cloud FPS with two clouds per SM, multi-tile Correlation3D CTAs).  The first
+    and the last sample of every output are compared with the CPU oracle: indices exactly, floats at the SURVEY §8a
+    tolerances."""
     import numpy as np
     from oracle import spec
     from rpeflow_b200 import pwc3d
     dev = torch.device("cuda", 0)
     cfg = CONFIGS["things"]
-    B = 74
+    from rpeflow_b200.workload import BENCH_BATCH
+    B = BENCH_BATCH
     host = make_host_inputs(cfg, B)
     stack = CostVolumeStack(cfg, dev)
     x = to_device(host, dev)
