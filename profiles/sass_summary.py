@@ -24,7 +24,7 @@ for line in out.splitlines():
         op = m.group(1)
         counts[kern]["_all"] += 1
         for w, _ in WANT:
-            if op == w or (w == "RED" and op == "RED"):
+            if op == w or (w == "REDUX" and op == "CREDUX"):          # CREDUX = redux.sync min/max (result in a uniform register)
                 counts[kern][w] += 1
                 total[w] += 1
 print("# SASS evidence — `cuobjdump -sass rpeflow_b200/libb200flow.so` (sm_100a), instruction counts per kernel\n")
